@@ -1,0 +1,161 @@
+/* svdb200.h -- C ABI of the B200-native SVDSolver hot path
+ * (dense -> band -> bidiagonal -> singular values; float and double).
+ *
+ * The reference (scrose/SVDSolver) has no FFI layer: its boundary is the C++ function level
+ * (SURVEY 8b).  Each entry point below names the reference function it replaces (file:line under
+ * the reference tree); include/svdb200_matrix.hpp carries the source-compatible C++ adapters
+ * (csc586::gpu::cuda_brd_p1, csc586::parallel::brd_p1/brd_p2, csc586::serial::qrd) on top of it.
+ *
+ * Conventions
+ *   - matrices are square n x n, dense ROW-MAJOR (what Matrix::flatten() yields, matrix.h:258,
+ *     svd_cuda_2.cu:549), band | n, updated in place unless stated;
+ *   - every function returns an int status: 0 ok, <0 argument/shape error (SVDB200_E_*),
+ *     >0 a CUDA / NCCL error code offset by SVDB200_CUDA_ERR / SVDB200_NCCL_ERR;
+ *     no exceptions cross this boundary (the reference assert()s and ignores CUDA errors);
+ *   - the caller owns host buffers; the handle owns a reusable device workspace and one stream;
+ *     one handle per host thread / GPU, re-entrant across handles;
+ *   - "_dev" variants take device pointers (inputs already resident in HBM) and enqueue on the
+ *     handle's stream without synchronising; host-pointer variants copy H2D/D2H inside the call
+ *     and return after completion, like the reference's timed region (timing.h:78-83).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with a status.
+ */
+#ifndef SVDB200_H
+#define SVDB200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svdb200_ctx* svdb200_handle;
+
+enum { SVDB200_F32 = 0, SVDB200_F64 = 1 };
+
+/* Elimination order of stage 1.
+ *   PANEL: full-height panel QR / full-width panel LQ + compact-WY trailing update -- the order of
+ *          csc586::gpu::cuda_brd_p1 (svd_cuda_1.cu:750, svd_cuda_2.cu:1117) and of its CPU twin
+ *          csc586::gpu::brd_p1 (svd_cpu.h:370).  The throughput path.
+ *   TILE : flat-tree tile QR/LQ in the exact task order and arithmetic order of
+ *          csc586::parallel::brd_p1 (svd_parallel.h:411-533); reproduces data/band_* including the
+ *          sign of every band entry (SURVEY 8a'). */
+enum { SVDB200_ORDER_PANEL = 0, SVDB200_ORDER_TILE = 1 };
+
+enum {
+    SVDB200_OK = 0,
+    SVDB200_E_ARG = -1,        /* null pointer / bad enum */
+    SVDB200_E_SHAPE = -2,      /* m != n, band == 0, n % band != 0 (matrix.h:407 needs t | n) */
+    SVDB200_E_CAPACITY = -3,   /* exceeds what the handle was created for / what the kernel supports */
+    SVDB200_E_NODEVICE = -4,   /* no usable CUDA device: there is no CPU fallback */
+    SVDB200_E_NOCONV = -5,     /* QR diagonalisation hit max_iter (svd_serial.h:419) */
+    SVDB200_E_STATE = -6,
+    SVDB200_CUDA_ERR = 1000,   /* status = 1000 + cudaError_t */
+    SVDB200_NCCL_ERR = 2000    /* status = 2000 + ncclResult_t */
+};
+
+int svdb200_version(void);
+const char* svdb200_strerror(int status);
+/* Last CUDA / NCCL error string seen by this handle (empty if none). */
+const char* svdb200_last_error(svdb200_handle h);
+
+/* Workspace for matrices up to max_n x max_n with band `band`, element type dtype.
+ * Replaces the per-call cudaMalloc of the 6*n^2 arena (svd_cuda_2.cu:1126-1133). */
+int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, int dtype);
+int svdb200_destroy(svdb200_handle h);
+/* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*); NULL restores the
+ * handle's own stream.  Lets a harness bracket the work with its own CUDA events. */
+int svdb200_set_stream(svdb200_handle h, void* cuda_stream);
+int svdb200_synchronize(svdb200_handle h);
+
+/* ---- Stage 1: dense -> band (b+1 diagonals) -----------------------------------------------
+ * Replaces csc586::gpu::cuda_brd_p1 (svd_cuda_2.cu:1117; order=PANEL) and
+ * csc586::parallel::brd_p1<T> (svd_parallel.h:411; order=TILE).  `a` (n x n) is overwritten by
+ * the band matrix (the reference mutates A in place and also returns it). */
+int svdb200_dense_to_band_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, int order);
+int svdb200_dense_to_band_f64(svdb200_handle h, double* a, size_t m, size_t n, size_t band, int order);
+int svdb200_dense_to_band_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, int order);
+int svdb200_dense_to_band_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, int order);
+
+/* ---- Stage 2: band -> bidiagonal ------------------------------------------------------------
+ * Replaces csc586::parallel::brd_p2<T>(A, band) (svd_parallel.h:640-695) == gpu::brd_p2(A, band+1)
+ * (svd_cpu.h:631).  Same window schedule (boundary behaviour included) and the same arithmetic
+ * order, so that the result is bit-identical to the reference.  `a` is updated in place (the
+ * reference leaves the full matrix updated); d (n) and e (n-1) receive diag(A), diag(A,1). */
+int svdb200_band_to_bidiag_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, float* d, float* e);
+int svdb200_band_to_bidiag_f64(svdb200_handle h, double* a, size_t m, size_t n, size_t band, double* d, double* e);
+int svdb200_band_to_bidiag_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, float* d_dev, float* e_dev);
+int svdb200_band_to_bidiag_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, double* d_dev, double* e_dev);
+
+/* ---- QR diagonalisation of the bidiagonal ----------------------------------------------------
+ * Replaces csc586::serial::qrd<T> (svd_serial.h:368-422): Demmel-Kahan implicit zero-shift QR
+ * sweeps (314-333) with the reference's convergence criteria (138-166), |sigma| sorted
+ * descending.  d (n), e (n-1) are inputs; sigma (n) the output; *sweeps (optional) the number of
+ * sweeps run.  The reference only compiles for float; the double entry point is the same
+ * algorithm in double. */
+int svdb200_bidiag_qr_f32(svdb200_handle h, const float* d, const float* e, size_t n, float* sigma, long long* sweeps);
+int svdb200_bidiag_qr_f64(svdb200_handle h, const double* d, const double* e, size_t n, double* sigma, long long* sweeps);
+int svdb200_bidiag_qr_dev_f32(svdb200_handle h, float* d_dev, float* e_dev, size_t n, float* sigma_dev);
+int svdb200_bidiag_qr_dev_f64(svdb200_handle h, double* d_dev, double* e_dev, size_t n, double* sigma_dev);
+
+/* ---- Fused chain: singular values of a dense matrix ------------------------------
+ * dense -> brd_p1 -> brd_p2 -> qrd.  `a` is overwritten by the bidiagonalised matrix. */
+int svdb200_svdvals_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, int order, float* sigma);
+int svdb200_svdvals_f64(svdb200_handle h, double* a, size_t m, size_t n, size_t band, int order, double* sigma);
+int svdb200_svdvals_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, int order, float* sigma_dev);
+int svdb200_svdvals_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, int order, double* sigma_dev);
+
+/* ---- Batched small matrices (BASELINE config 5) ------------------------------------------------
+ * `count` independent n x n matrices stored back to back; sigma is count x n.  One matrix per
+ * CTA-resident pipeline; shards by matrix across GPUs (one handle per GPU). */
+int svdb200_svdvals_batched_f32(svdb200_handle h, float* a, size_t count, size_t n, size_t band, float* sigma);
+int svdb200_svdvals_batched_f64(svdb200_handle h, double* a, size_t count, size_t n, size_t band, double* sigma);
+int svdb200_svdvals_batched_dev_f32(svdb200_handle h, float* a_dev, size_t count, size_t n, size_t band, float* sigma_dev);
+int svdb200_svdvals_batched_dev_f64(svdb200_handle h, double* a_dev, size_t count, size_t n, size_t band, double* sigma_dev);
+
+/* ---- Measurement helpers ------------------------------------------------------------------------
+ * Device time (CUDA events on the handle's stream) of the stages of the LAST host-pointer call, ms.
+ * stage-1 sub-times: panel factorisations vs trailing updates are reported by svdb200_stage1_profile. */
+int svdb200_last_timings(svdb200_handle h, double* ms_stage1, double* ms_stage2, double* ms_qr, double* ms_h2d, double* ms_d2h);
+/* Number of kernel launches issued by this handle since creation (the bench's gpu_launches). */
+long long svdb200_launch_count(svdb200_handle h);
+/* reference error metric gpu::Matrix<T>::mse (matrix_gpu.h:438-453), evaluated on the device. */
+int svdb200_mse_f32(svdb200_handle h, const float* a, const float* b, size_t n, size_t band, float* out);
+int svdb200_mse_f64(svdb200_handle h, const double* a, const double* b, size_t n, size_t band, double* out);
+/* Deterministic U[lo,hi) fill of a DEVICE buffer (svdsolver_b200/synth.py documents the stream);
+ * replaces matrix_generator / Matrix::fill(min,max) (svd_cuda_2.cu:1230, matrix_gpu.h:336). */
+int svdb200_fill_uniform_dev_f32(svdb200_handle h, float* a_dev, size_t count, unsigned long long seed, double lo, double hi);
+int svdb200_fill_uniform_dev_f64(svdb200_handle h, double* a_dev, size_t count, unsigned long long seed, double lo, double hi);
+/* Register-resident FP64 (DMMA mma.sync m8n8k4 / DFMA) and FP32 (FFMA) peak probes: TFLOP/s. kind:
+ * 0 = DFMA, 1 = DMMA f64, 2 = FFMA, 3 = TF32 mma.sync.  Used as roofline denominators. */
+int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops);
+
+/* Trailing-update building blocks, exposed for parity tests and kernel-level benchmarks
+ * (qr_apply / lq_apply, svd_parallel.h:243-281): all device pointers, row-major.
+ *   W(b x ncols)   = V(mrows x b)^T * C(mrows x ncols)          [ldc]
+ *   C(mrows x ncols) += P(mrows x b) * Q(b x ncols)
+ *   W(mrows x b)   = C(mrows x ncols) * Ut(ncols x b) */
+int svdb200_gemm_tn_dev_f32(svdb200_handle h, const float* v, const float* c, size_t ldc, size_t mrows, size_t ncols, size_t b, float* w);
+int svdb200_gemm_tn_dev_f64(svdb200_handle h, const double* v, const double* c, size_t ldc, size_t mrows, size_t ncols, size_t b, double* w);
+int svdb200_rank_update_dev_f32(svdb200_handle h, float* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const float* p, const float* q, size_t ldq);
+int svdb200_rank_update_dev_f64(svdb200_handle h, double* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const double* p, const double* q, size_t ldq);
+int svdb200_gemm_nn_dev_f32(svdb200_handle h, const float* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const float* ut, float* w);
+int svdb200_gemm_nn_dev_f64(svdb200_handle h, const double* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const double* ut, double* w);
+
+/* ---- Multi-GPU stage 1 (BASELINE config 4): 1-D block-cyclic over columns, one process per GPU.
+ * nccl_unique_id: the 128-byte ncclUniqueId produced by svdb200_dist_unique_id on rank 0 and
+ * broadcast by the launcher (torch.distributed / MPI / a file).  a_local holds this rank's block
+ * columns: global block-column j (width band) lives on rank j % nranks at local block j / nranks;
+ * storage is row-major n x ncols_local. */
+typedef struct svdb200_dist_ctx* svdb200_dist_handle;
+int svdb200_dist_unique_id(void* out128);
+int svdb200_dist_create(svdb200_dist_handle* out, int device, int rank, int nranks, const void* nccl_unique_id,
+                        size_t n, size_t band, int dtype);
+int svdb200_dist_destroy(svdb200_dist_handle h);
+size_t svdb200_dist_local_cols(size_t n, size_t band, int rank, int nranks);
+int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle h, float* a_local_dev, size_t n, size_t band);
+int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle h, double* a_local_dev, size_t n, size_t band);
+int svdb200_dist_set_stream(svdb200_dist_handle h, void* cuda_stream);
+long long svdb200_dist_launch_count(svdb200_dist_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDB200_H */

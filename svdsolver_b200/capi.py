@@ -1,0 +1,194 @@
+"""ctypes binding of libsvdb200.so -- the C-ABI declared in include/svdb200.h.
+
+This is the host-side mirror used by tests/ and bench.py; it never falls back to the CPU: if the
+library is missing, or no CUDA device is usable, every call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsvdb200.so")
+
+F32, F64 = 0, 1
+ORDER_PANEL, ORDER_TILE = 0, 1
+
+_lib = None
+
+
+class SvdB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"svdb200 status {status}: {msg}")
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvdB200Error(-100, f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                     "(there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.svdb200_strerror.restype = ctypes.c_char_p
+        _lib.svdb200_last_error.restype = ctypes.c_char_p
+        _lib.svdb200_last_error.argtypes = [ctypes.c_void_p]
+        _lib.svdb200_launch_count.restype = ctypes.c_longlong
+        _lib.svdb200_launch_count.argtypes = [ctypes.c_void_p]
+        _lib.svdb200_dist_local_cols.restype = ctypes.c_size_t
+        _lib.svdb200_dist_launch_count.restype = ctypes.c_longlong
+    return _lib
+
+
+def _suf(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32", F32
+    if dtype == np.float64:
+        return "f64", F64
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+Z = ctypes.c_size_t
+
+
+class Handle:
+    """svdb200_handle: workspace for matrices up to max_n x max_n with band `band`."""
+
+    def __init__(self, max_n, band, dtype, device=0):
+        self.suf, self.code = _suf(dtype)
+        self.dtype = np.dtype(dtype)
+        self.max_n, self.band = int(max_n), int(band)
+        self.h = ctypes.c_void_p()
+        st = lib().svdb200_create(ctypes.byref(self.h), ctypes.c_int(device), Z(max_n), Z(band), ctypes.c_int(self.code))
+        if st != 0:
+            self.h = ctypes.c_void_p()
+            raise SvdB200Error(st, lib().svdb200_strerror(st).decode())
+
+    def close(self):
+        if self.h:
+            lib().svdb200_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st):
+        if st != 0:
+            extra = lib().svdb200_last_error(self.h).decode()
+            raise SvdB200Error(st, lib().svdb200_strerror(st).decode() + (f" [{extra}]" if extra else ""))
+
+    def _fn(self, name):
+        return getattr(lib(), f"svdb200_{name}_{self.suf}")
+
+    def _mat(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype).copy()
+        if a.ndim != 2:
+            raise ValueError("matrix expected")
+        return a
+
+    # ---- host-pointer API (H2D/D2H inside the call, like the reference's timed region) ----
+    def dense_to_band(self, a, band, order=ORDER_PANEL):
+        a = self._mat(a)
+        self._check(self._fn("dense_to_band")(self.h, _p(a), Z(a.shape[0]), Z(a.shape[1]), Z(band), ctypes.c_int(order)))
+        return a
+
+    def band_to_bidiag(self, a, band):
+        a = self._mat(a)
+        n = a.shape[1]
+        d = np.zeros(n, self.dtype)
+        e = np.zeros(max(n - 1, 0), self.dtype)
+        self._check(self._fn("band_to_bidiag")(self.h, _p(a), Z(a.shape[0]), Z(n), Z(band), _p(d), _p(e)))
+        return a, d, e
+
+    def bidiag_qr(self, d, e):
+        d = np.ascontiguousarray(d, dtype=self.dtype)
+        e = np.ascontiguousarray(e, dtype=self.dtype)
+        sigma = np.zeros(d.shape[0], self.dtype)
+        sweeps = ctypes.c_longlong(0)
+        self._check(self._fn("bidiag_qr")(self.h, _p(d), _p(e), Z(d.shape[0]), _p(sigma), ctypes.byref(sweeps)))
+        return sigma, int(sweeps.value)
+
+    def svdvals(self, a, band, order=ORDER_PANEL):
+        a = self._mat(a)
+        sigma = np.zeros(a.shape[1], self.dtype)
+        self._check(self._fn("svdvals")(self.h, _p(a), Z(a.shape[0]), Z(a.shape[1]), Z(band), ctypes.c_int(order), _p(sigma)))
+        return sigma, a
+
+    def svdvals_batched(self, a, band):
+        a = np.ascontiguousarray(a, dtype=self.dtype).copy()
+        count, n, _ = a.shape
+        sigma = np.zeros((count, n), self.dtype)
+        self._check(self._fn("svdvals_batched")(self.h, _p(a), Z(count), Z(n), Z(band), _p(sigma)))
+        return sigma
+
+    def mse(self, a, b, band):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        b = np.ascontiguousarray(b, dtype=self.dtype)
+        out = np.zeros(1, self.dtype)
+        self._check(self._fn("mse")(self.h, _p(a), _p(b), Z(a.shape[0]), Z(band), _p(out)))
+        return float(out[0])
+
+    # ---- device-pointer API (integers = CUdeviceptr, e.g. torch.Tensor.data_ptr()) ----
+    def set_stream(self, stream_ptr):
+        self._check(lib().svdb200_set_stream(self.h, ctypes.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._check(lib().svdb200_synchronize(self.h))
+
+    def dense_to_band_dev(self, a_ptr, n, band, order=ORDER_PANEL):
+        self._check(self._fn("dense_to_band_dev")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order)))
+
+    def band_to_bidiag_dev(self, a_ptr, n, band, d_ptr, e_ptr):
+        self._check(self._fn("band_to_bidiag_dev")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), _p(d_ptr), _p(e_ptr)))
+
+    def bidiag_qr_dev(self, d_ptr, e_ptr, n, sigma_ptr):
+        self._check(self._fn("bidiag_qr_dev")(self.h, _p(d_ptr), _p(e_ptr), Z(n), _p(sigma_ptr)))
+
+    def svdvals_dev(self, a_ptr, n, band, sigma_ptr, order=ORDER_PANEL):
+        self._check(self._fn("svdvals_dev")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order), _p(sigma_ptr)))
+
+    def svdvals_batched_dev(self, a_ptr, count, n, band, sigma_ptr):
+        self._check(self._fn("svdvals_batched_dev")(self.h, _p(a_ptr), Z(count), Z(n), Z(band), _p(sigma_ptr)))
+
+    def fill_uniform_dev(self, a_ptr, count, seed, lo=0.0, hi=5.0):
+        self._check(self._fn("fill_uniform_dev")(self.h, _p(a_ptr), Z(count), ctypes.c_ulonglong(seed), ctypes.c_double(lo), ctypes.c_double(hi)))
+
+    def gemm_tn_dev(self, v_ptr, c_ptr, ldc, mrows, ncols, b, w_ptr):
+        self._check(self._fn("gemm_tn_dev")(self.h, _p(v_ptr), _p(c_ptr), Z(ldc), Z(mrows), Z(ncols), Z(b), _p(w_ptr)))
+
+    def gemm_nn_dev(self, c_ptr, ldc, mrows, ncols, b, ut_ptr, w_ptr):
+        self._check(self._fn("gemm_nn_dev")(self.h, _p(c_ptr), Z(ldc), Z(mrows), Z(ncols), Z(b), _p(ut_ptr), _p(w_ptr)))
+
+    def rank_update_dev(self, c_ptr, ldc, mrows, ncols, b, p_ptr, q_ptr, ldq):
+        self._check(self._fn("rank_update_dev")(self.h, _p(c_ptr), Z(ldc), Z(mrows), Z(ncols), Z(b), _p(p_ptr), _p(q_ptr), Z(ldq)))
+
+    def last_timings(self):
+        v = [ctypes.c_double(0) for _ in range(5)]
+        self._check(lib().svdb200_last_timings(self.h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("stage1_ms", "stage2_ms", "qr_ms", "h2d_ms", "d2h_ms"), [x.value for x in v]))
+
+    def launch_count(self):
+        return int(lib().svdb200_launch_count(self.h))
+
+    def probe_peak(self, kind):
+        out = ctypes.c_double(0)
+        self._check(lib().svdb200_probe_peak(self.h, ctypes.c_int(kind), ctypes.byref(out)))
+        return out.value

@@ -1,0 +1,525 @@
+// C ABI of libsvdb200.so (declared in include/svdb200.h).  Thin: argument checks, workspace
+// ownership, host<->device staging and CUDA-event timing; all arithmetic lives in the kernels.
+#include <new>
+#include "common.cuh"
+
+using namespace svdb200;
+
+namespace svdb200 {
+namespace {
+
+// ---- small utility kernels ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// element i = lo + (hi-lo) * (splitmix64(seed+i) >> 11) * 2^-53, evaluated in double, rounded to T
+// (svdsolver_b200/synth.py is the host mirror).  No FMA contraction so host and device agree bitwise.
+template <typename T>
+__global__ void fill_uniform_kernel(T* __restrict__ a, size_t count, unsigned long long seed, double lo, double hi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double span = __dsub_rn(hi, lo);
+    for (; i < count; i += stride) {
+        double u = __dmul_rn((double)(splitmix64(seed + i) >> 11), 1.0 / 9007199254740992.0);
+        a[i] = (T)__dadd_rn(lo, __dmul_rn(span, u));
+    }
+}
+
+// gpu::Matrix<T>::mse (matrix_gpu.h:438-453): sum over i, j in [i, min(i+band, n)) of | |a|-|b| |,
+// divided by band*nrows.  (The reference accumulates in float in row order; this is a reported
+// metric, not a parity target, so a tree reduction in double is used.)
+template <typename T>
+__global__ void mse_kernel(const T* __restrict__ a, const T* __restrict__ b, int n, int band, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * band; e += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(e / band), j = i + (int)(e % band);
+        if (j < n) acc += fabs(fabs((double)a[(size_t)i * n + j]) - fabs((double)b[(size_t)i * n + j]));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, sh[0]);
+}
+
+// ---- register-resident peak probes (roofline denominators) -----------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) peak_kernel(double* sink, int iters) {
+    const int lane = threadIdx.x & 31;
+    if (KIND == 0) {                       // DFMA: 8 independent chains
+        double a = 1.0 + lane * 1e-9, b = 0.999999, c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fma(a, b, c[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fma(c[i], b, a);
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += c[i];
+        if (s == 123.456) sink[0] = s;
+    } else if (KIND == 1) {                // DMMA m8n8k4: 8 independent accumulator tiles
+        double a = 1.0 + lane * 1e-9, b = 0.5, c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = 0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[2 * i]), "+d"(c[2 * i + 1]) : "d"(a), "d"(b));
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i];
+        if (s == 123.456) sink[0] = s;
+    } else if (KIND == 2) {                // FFMA
+        float a = 1.0f + lane * 1e-6f, b = 0.99999f, c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = (float)i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fmaf(a, b, c[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fmaf(c[i], b, a);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += c[i];
+        if (s == 123.456f) sink[0] = s;
+    } else {                               // TF32 mma.sync m16n8k8
+        uint32_t a[4] = {0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u}, b[2] = {0x3f000000u, 0x3f000000u};
+        float c[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c[i] = 0.f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(c[4 * i]), "+f"(c[4 * i + 1]), "+f"(c[4 * i + 2]), "+f"(c[4 * i + 3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += c[i];
+        if (s == 123.456f) sink[0] = s;
+    }
+}
+
+}  // namespace
+
+template <typename T>
+int fill_uniform(Ctx* c, T* a, size_t count, unsigned long long seed, double lo, double hi) {
+    if (count == 0) return 0;
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    fill_uniform_kernel<T><<<blocks, 256, 0, c->stream>>>(a, count, seed, lo, hi);
+    SVDB_CHECK(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+template int fill_uniform<float>(Ctx*, float*, size_t, unsigned long long, double, double);
+template int fill_uniform<double>(Ctx*, double*, size_t, unsigned long long, double, double);
+
+template <typename T>
+int mse_metric(Ctx* c, const T* a, const T* b, size_t n, size_t band, T* out_host) {
+    double* acc = reinterpret_cast<double*>(c->qr_info + 4);
+    SVDB_CHECK(c, cudaMemsetAsync(acc, 0, sizeof(double), c->stream));
+    mse_kernel<T><<<148, 256, 0, c->stream>>>(a, b, (int)n, (int)band, acc);
+    SVDB_CHECK(c, cudaGetLastError());
+    c->launches++;
+    double h = 0;
+    SVDB_CHECK(c, cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVDB_CHECK(c, cudaStreamSynchronize(c->stream));
+    *out_host = (T)(h / ((double)band * (double)n));
+    return 0;
+}
+template int mse_metric<float>(Ctx*, const float*, const float*, size_t, size_t, float*);
+template int mse_metric<double>(Ctx*, const double*, const double*, size_t, size_t, double*);
+
+int probe_peak(Ctx* c, int kind, double* tflops) {
+    if (kind < 0 || kind > 3 || !tflops) return SVDB200_E_ARG;
+    double* sink = reinterpret_cast<double*>(c->qr_info + 4);
+    const int iters = 20000, blocks = c->num_sms * 8, threads = 256;
+    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        SVDB_CHECK(c, cudaEventRecord(e0, c->stream));
+        switch (kind) {
+            case 0: peak_kernel<0><<<blocks, threads, 0, c->stream>>>(sink, iters); break;
+            case 1: peak_kernel<1><<<blocks, threads, 0, c->stream>>>(sink, iters); break;
+            case 2: peak_kernel<2><<<blocks, threads, 0, c->stream>>>(sink, iters); break;
+            default: peak_kernel<3><<<blocks, threads, 0, c->stream>>>(sink, iters); break;
+        }
+        SVDB_CHECK(c, cudaGetLastError());
+        c->launches++;
+        SVDB_CHECK(c, cudaEventRecord(e1, c->stream));
+        SVDB_CHECK(c, cudaEventSynchronize(e1));
+        float ms = 0;
+        SVDB_CHECK(c, cudaEventElapsedTime(&ms, e0, e1));
+        double flops;
+        if (kind == 0 || kind == 2) flops = (double)blocks * threads * iters * 16.0 * 2.0;
+        else if (kind == 1) flops = (double)blocks * (threads / 32) * iters * 8.0 * (8.0 * 8.0 * 4.0 * 2.0);
+        else flops = (double)blocks * (threads / 32) * iters * 8.0 * (16.0 * 8.0 * 8.0 * 2.0);
+        double tf = flops / (ms * 1e-3) * 1e-12;
+        if (tf > best) best = tf;
+    }
+    *tflops = best;
+    return 0;
+}
+
+// Batched driver, first version: one pipeline instance per matrix on the handle's stream.
+template <typename T>
+int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
+    T* d = reinterpret_cast<T*>(c->d);
+    T* e = reinterpret_cast<T*>(c->e);
+    for (size_t i = 0; i < count; ++i) {
+        T* ai = a + i * n * n;
+        SVDB_TRY(stage1_panel_order<T>(c, ai, n, band));
+        SVDB_TRY(stage2_chase<T>(c, ai, n, band, d, e));
+        SVDB_TRY(bidiag_qr<T>(c, d, e, n, sigma + i * n));
+    }
+    return 0;
+}
+template int batched_svdvals<float>(Ctx*, float*, size_t, size_t, size_t, float*);
+template int batched_svdvals<double>(Ctx*, double*, size_t, size_t, size_t, double*);
+
+}  // namespace svdb200
+
+// ======================================================================================================
+namespace {
+
+template <typename T> constexpr int dtype_of();
+template <> constexpr int dtype_of<float>() { return SVDB200_F32; }
+template <> constexpr int dtype_of<double>() { return SVDB200_F64; }
+
+int check_square(Ctx* c, size_t m, size_t n, size_t band, int dtype) {
+    if (!c) return SVDB200_E_ARG;
+    if (c->dtype != dtype) return SVDB200_E_ARG;
+    if (m != n || band == 0 || n == 0 || n % band != 0) return SVDB200_E_SHAPE;
+    if (n > c->max_n || band > c->band) return SVDB200_E_CAPACITY;
+    return 0;
+}
+
+template <typename T>
+int stage1_dispatch(Ctx* c, T* a_dev, size_t n, size_t band, int order) {
+    if (order == SVDB200_ORDER_PANEL) return stage1_panel_order<T>(c, a_dev, n, band);
+    if (order == SVDB200_ORDER_TILE) return stage1_tile_order<T>(c, a_dev, n, band);
+    return SVDB200_E_ARG;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// Host-pointer chain with per-stage CUDA-event timing.  what: bit0 stage1, bit1 stage2, bit2 qr.
+template <typename T>
+int host_chain(Ctx* c, T* a, size_t n, size_t band, int order, int what, T* d, T* e, T* sigma, long long* sweeps) {
+    T* ad = reinterpret_cast<T*>(c->a_dev);
+    T* dd = reinterpret_cast<T*>(c->d);
+    T* ed = reinterpret_cast<T*>(c->e);
+    T* sd = reinterpret_cast<T*>(c->sigma);
+    cudaStream_t s = c->stream;
+    c->ms_stage1 = c->ms_stage2 = c->ms_qr = c->ms_h2d = c->ms_d2h = 0;
+    SVDB_CHECK(c, cudaEventRecord(c->ev[0], s));
+    if (what & 3) SVDB_CHECK(c, cudaMemcpyAsync(ad, a, sizeof(T) * n * n, cudaMemcpyHostToDevice, s));
+    if (!(what & 3) && (what & 4)) {
+        SVDB_CHECK(c, cudaMemcpyAsync(dd, d, sizeof(T) * n, cudaMemcpyHostToDevice, s));
+        SVDB_CHECK(c, cudaMemcpyAsync(ed, e, sizeof(T) * (n - 1), cudaMemcpyHostToDevice, s));
+    }
+    SVDB_CHECK(c, cudaEventRecord(c->ev[1], s));
+    if (what & 1) SVDB_TRY(stage1_dispatch<T>(c, ad, n, band, order));
+    SVDB_CHECK(c, cudaEventRecord(c->ev[2], s));
+    if (what & 2) SVDB_TRY(stage2_chase<T>(c, ad, n, band, dd, ed));
+    SVDB_CHECK(c, cudaEventRecord(c->ev[3], s));
+    if (what & 4) SVDB_TRY(bidiag_qr<T>(c, dd, ed, n, sd));
+    SVDB_CHECK(c, cudaEventRecord(c->ev[4], s));
+    if ((what & 3) && a) SVDB_CHECK(c, cudaMemcpyAsync(a, ad, sizeof(T) * n * n, cudaMemcpyDeviceToHost, s));
+    if ((what & 2) && !(what & 4)) {
+        if (d) SVDB_CHECK(c, cudaMemcpyAsync(d, dd, sizeof(T) * n, cudaMemcpyDeviceToHost, s));
+        if (e) SVDB_CHECK(c, cudaMemcpyAsync(e, ed, sizeof(T) * (n - 1), cudaMemcpyDeviceToHost, s));
+    }
+    long long info[3] = {0, 0, 0};
+    if (what & 4) {
+        SVDB_CHECK(c, cudaMemcpyAsync(sigma, sd, sizeof(T) * n, cudaMemcpyDeviceToHost, s));
+        SVDB_CHECK(c, cudaMemcpyAsync(info, c->qr_info, sizeof(info), cudaMemcpyDeviceToHost, s));
+    }
+    SVDB_CHECK(c, cudaEventRecord(c->ev[5], s));
+    SVDB_CHECK(c, cudaStreamSynchronize(s));
+    c->ms_h2d = elapsed(c->ev[0], c->ev[1]);
+    c->ms_stage1 = elapsed(c->ev[1], c->ev[2]);
+    c->ms_stage2 = elapsed(c->ev[2], c->ev[3]);
+    c->ms_qr = elapsed(c->ev[3], c->ev[4]);
+    c->ms_d2h = elapsed(c->ev[4], c->ev[5]);
+    if (what & 4) {
+        if (sweeps) *sweeps = info[0];
+        if (info[1] != 0) return SVDB200_E_NOCONV;
+    }
+    return 0;
+}
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int svdb200_version(void) { return 100; }
+
+const char* svdb200_strerror(int s) {
+    switch (s) {
+        case SVDB200_OK: return "ok";
+        case SVDB200_E_ARG: return "invalid argument";
+        case SVDB200_E_SHAPE: return "shape error: need square n x n with band | n";
+        case SVDB200_E_CAPACITY: return "exceeds handle capacity or kernel limits";
+        case SVDB200_E_NODEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case SVDB200_E_NOCONV: return "QR diagonalisation reached max_iter";
+        case SVDB200_E_STATE: return "invalid state";
+        default: break;
+    }
+    if (s >= SVDB200_NCCL_ERR) return "NCCL error";
+    if (s >= SVDB200_CUDA_ERR) return cudaGetErrorString((cudaError_t)(s - SVDB200_CUDA_ERR));
+    return "unknown status";
+}
+
+const char* svdb200_last_error(svdb200_handle h) {
+    return h ? reinterpret_cast<Ctx*>(h)->last_error.c_str() : "";
+}
+
+int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, int dtype) {
+    if (!out || (dtype != SVDB200_F32 && dtype != SVDB200_F64)) return SVDB200_E_ARG;
+    if (max_n == 0 || band == 0 || band > (size_t)kMaxBand) return SVDB200_E_SHAPE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return SVDB200_E_NODEVICE;
+    }
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return SVDB200_E_STATE;
+    c->device = device; c->dtype = dtype; c->max_n = max_n; c->band = band;
+    c->esz = dtype == SVDB200_F32 ? 4 : 8;
+#define SVDB_CREATE_CHECK(expr)                                         \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) {                                        \
+            int _s = cuda_status(c, _e, #expr);                         \
+            svdb200_destroy(reinterpret_cast<svdb200_handle>(c));       \
+            return _s;                                                  \
+        }                                                               \
+    } while (0)
+    SVDB_CREATE_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SVDB_CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { delete c; return SVDB200_E_NODEVICE; }   // sm_100a code only
+    c->num_sms = prop.multiProcessorCount;
+    c->coop_supported = prop.cooperativeLaunch;
+    SVDB_CREATE_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& e : c->ev) SVDB_CREATE_CHECK(cudaEventCreate(&e));
+    const size_t es = c->esz, nb = round_up(max_n, 128) + 128;
+    SVDB_CREATE_CHECK(cudaMalloc(&c->a_dev, es * max_n * max_n));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->v, es * nb * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->v2, es * nb * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->w, es * nb * band));
+    c->wpart_elems = 16 * nb * band;
+    if (c->wpart_elems < 4 * nb) c->wpart_elems = 4 * nb;
+    SVDB_CREATE_CHECK(cudaMalloc(&c->wpart, es * c->wpart_elems));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->s, es * band * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->tau, es * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->red, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->bar, 64));
+    SVDB_CREATE_CHECK(cudaMemset(c->bar, 0, 64));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->prog, sizeof(int) * (max_n + 8)));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->d, es * (max_n + 8)));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->e, es * (max_n + 8)));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->sigma, es * (max_n + 8)));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->qr_info, 64));
+    SVDB_CREATE_CHECK(cudaMemset(c->qr_info, 0, 64));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->tileq, es * (max_n / band + 2) * 4 * band * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->tilestate, es * (4 * band * band + 64)));
+#undef SVDB_CREATE_CHECK
+    *out = reinterpret_cast<svdb200_handle>(c);
+    return 0;
+}
+
+int svdb200_destroy(svdb200_handle h) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    void* ptrs[] = {c->a_dev, c->v, c->v2, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
+                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int svdb200_set_stream(svdb200_handle h, void* stream) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->own_stream;
+    return 0;
+}
+
+int svdb200_synchronize(svdb200_handle h) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    SVDB_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+#define SVDB_ENTER(T)                                    \
+    Ctx* c = reinterpret_cast<Ctx*>(h);                  \
+    if (!c) return SVDB200_E_ARG;                        \
+    if (c->dtype != dtype_of<T>()) return SVDB200_E_ARG; \
+    SVDB_CHECK(c, cudaSetDevice(c->device));
+
+#define SVDB_DEFINE_TYPED(T, S)                                                                                          \
+    int svdb200_dense_to_band_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order) {                  \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        return host_chain<T>(c, a, n, band, order, 1, nullptr, nullptr, nullptr, nullptr);                               \
+    }                                                                                                                    \
+    int svdb200_dense_to_band_dev_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order) {              \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        return stage1_dispatch<T>(c, a, n, band, order);                                                                 \
+    }                                                                                                                    \
+    int svdb200_band_to_bidiag_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, T* d, T* e) {                \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, 1, dtype_of<T>()));                                                               \
+        if (band == 0 || band > c->band) return SVDB200_E_CAPACITY;                                                      \
+        return host_chain<T>(c, a, n, band, 0, 2, d, e, nullptr, nullptr);                                               \
+    }                                                                                                                    \
+    int svdb200_band_to_bidiag_dev_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, T* d, T* e) {            \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, 1, dtype_of<T>()));                                                               \
+        if (band == 0 || band > c->band) return SVDB200_E_CAPACITY;                                                      \
+        return stage2_chase<T>(c, a, n, band, d, e);                                                                     \
+    }                                                                                                                    \
+    int svdb200_bidiag_qr_##S(svdb200_handle h, const T* d, const T* e, size_t n, T* sigma, long long* sweeps) {         \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!d || !e || !sigma) return SVDB200_E_ARG;                                                                    \
+        if (n < 2) return SVDB200_E_SHAPE;                                                                               \
+        if (n > c->max_n) return SVDB200_E_CAPACITY;                                                                     \
+        return host_chain<T>(c, nullptr, n, 1, 0, 4, const_cast<T*>(d), const_cast<T*>(e), sigma, sweeps);               \
+    }                                                                                                                    \
+    int svdb200_bidiag_qr_dev_##S(svdb200_handle h, T* d, T* e, size_t n, T* sigma) {                                    \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!d || !e || !sigma) return SVDB200_E_ARG;                                                                    \
+        if (n < 2) return SVDB200_E_SHAPE;                                                                               \
+        return bidiag_qr<T>(c, d, e, n, sigma);                                                                          \
+    }                                                                                                                    \
+    int svdb200_svdvals_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* sigma) {              \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !sigma) return SVDB200_E_ARG;                                                                          \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        return host_chain<T>(c, a, n, band, order, 7, nullptr, nullptr, sigma, nullptr);                                 \
+    }                                                                                                                    \
+    int svdb200_svdvals_dev_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* sigma) {          \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !sigma) return SVDB200_E_ARG;                                                                          \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        SVDB_TRY(stage1_dispatch<T>(c, a, n, band, order));                                                              \
+        SVDB_TRY(stage2_chase<T>(c, a, n, band, reinterpret_cast<T*>(c->d), reinterpret_cast<T*>(c->e)));                \
+        return bidiag_qr<T>(c, reinterpret_cast<T*>(c->d), reinterpret_cast<T*>(c->e), n, sigma);                        \
+    }                                                                                                                    \
+    int svdb200_svdvals_batched_dev_##S(svdb200_handle h, T* a, size_t count, size_t n, size_t band, T* sigma) {         \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !sigma) return SVDB200_E_ARG;                                                                          \
+        SVDB_TRY(check_square(c, n, n, band, dtype_of<T>()));                                                            \
+        return batched_svdvals<T>(c, a, count, n, band, sigma);                                                          \
+    }                                                                                                                    \
+    int svdb200_svdvals_batched_##S(svdb200_handle h, T* a, size_t count, size_t n, size_t band, T* sigma) {             \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !sigma) return SVDB200_E_ARG;                                                                          \
+        SVDB_TRY(check_square(c, n, n, band, dtype_of<T>()));                                                            \
+        T *ad = nullptr, *sd = nullptr;                                                                                  \
+        SVDB_CHECK(c, cudaMalloc(&ad, sizeof(T) * count * n * n));                                                       \
+        cudaError_t e2 = cudaMalloc(&sd, sizeof(T) * count * n);                                                         \
+        if (e2 != cudaSuccess) { cudaFree(ad); return cuda_status(c, e2, "cudaMalloc"); }                                \
+        int st = 0;                                                                                                      \
+        cudaError_t ce = cudaMemcpyAsync(ad, a, sizeof(T) * count * n * n, cudaMemcpyHostToDevice, c->stream);           \
+        if (ce == cudaSuccess) st = batched_svdvals<T>(c, ad, count, n, band, sd);                                       \
+        if (ce == cudaSuccess && st == 0) ce = cudaMemcpyAsync(sigma, sd, sizeof(T) * count * n, cudaMemcpyDeviceToHost, c->stream); \
+        if (ce == cudaSuccess && st == 0) ce = cudaMemcpyAsync(a, ad, sizeof(T) * count * n * n, cudaMemcpyDeviceToHost, c->stream); \
+        cudaError_t se = cudaStreamSynchronize(c->stream);                                                               \
+        cudaFree(ad); cudaFree(sd);                                                                                      \
+        if (st) return st;                                                                                               \
+        if (ce != cudaSuccess) return cuda_status(c, ce, "batched copy");                                                \
+        if (se != cudaSuccess) return cuda_status(c, se, "batched sync");                                                \
+        return 0;                                                                                                        \
+    }                                                                                                                    \
+    int svdb200_mse_##S(svdb200_handle h, const T* a, const T* b, size_t n, size_t band, T* out) {                       \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !b || !out || n == 0 || band == 0) return SVDB200_E_ARG;                                               \
+        if (n > c->max_n) return SVDB200_E_CAPACITY;                                                                     \
+        T* ad = reinterpret_cast<T*>(c->a_dev);                                                                          \
+        T* bd = nullptr;                                                                                                 \
+        SVDB_CHECK(c, cudaMalloc(&bd, sizeof(T) * n * n));                                                               \
+        cudaMemcpyAsync(ad, a, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream);                                    \
+        cudaMemcpyAsync(bd, b, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream);                                    \
+        int st = mse_metric<T>(c, ad, bd, n, band, out);                                                                 \
+        cudaFree(bd);                                                                                                    \
+        return st;                                                                                                       \
+    }                                                                                                                    \
+    int svdb200_fill_uniform_dev_##S(svdb200_handle h, T* a, size_t count, unsigned long long seed, double lo, double hi) { \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        return fill_uniform<T>(c, a, count, seed, lo, hi);                                                               \
+    }                                                                                                                    \
+    int svdb200_gemm_tn_dev_##S(svdb200_handle h, const T* v, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, T* w) { \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!v || !cm || !w) return SVDB200_E_ARG;                                                                       \
+        return gemm_tn<T>(c, v, cm, ldc, mrows, ncols, b, w);                                                            \
+    }                                                                                                                    \
+    int svdb200_rank_update_dev_##S(svdb200_handle h, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* p, const T* q, size_t ldq) { \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!cm || !p || !q) return SVDB200_E_ARG;                                                                       \
+        return rank_update<T>(c, cm, ldc, mrows, ncols, b, p, q, ldq);                                                   \
+    }                                                                                                                    \
+    int svdb200_gemm_nn_dev_##S(svdb200_handle h, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* ut, T* w) { \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!cm || !ut || !w) return SVDB200_E_ARG;                                                                      \
+        return gemm_nn<T>(c, cm, ldc, mrows, ncols, b, ut, w);                                                           \
+    }
+
+SVDB_DEFINE_TYPED(float, f32)
+SVDB_DEFINE_TYPED(double, f64)
+
+int svdb200_last_timings(svdb200_handle h, double* s1, double* s2, double* qr, double* h2d, double* d2h) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (s1) *s1 = c->ms_stage1;
+    if (s2) *s2 = c->ms_stage2;
+    if (qr) *qr = c->ms_qr;
+    if (h2d) *h2d = c->ms_h2d;
+    if (d2h) *d2h = c->ms_d2h;
+    return 0;
+}
+
+long long svdb200_launch_count(svdb200_handle h) { return h ? reinterpret_cast<Ctx*>(h)->launches : -1; }
+
+int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    SVDB_CHECK(c, cudaSetDevice(c->device));
+    return probe_peak(c, kind, tflops);
+}
+
+}  // extern "C"

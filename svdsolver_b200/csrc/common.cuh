@@ -1,0 +1,143 @@
+// Shared declarations of the svdb200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/svdb200.h"
+
+namespace svdb200 {
+
+constexpr int kMaxBand = 128;          // stage-1 panel width / stage-2 band supported by the kernels
+constexpr int kMaxPanelCtas = 148;     // one CTA per SM in the cooperative panel kernel
+
+struct Ctx {
+    int device = 0;
+    int dtype = SVDB200_F64;
+    size_t max_n = 0, band = 0, esz = 8;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device workspace (element type = dtype)
+    void* a_dev = nullptr;         // max_n * max_n : staging for host-pointer calls
+    void* v = nullptr;             // max_n * band  : V (QR) / U^T (LQ), row-major, unit diagonal explicit
+    void* v2 = nullptr;            // max_n * band  : V S^T (QR) ; band * max_n : S U (LQ)
+    void* w = nullptr;             // band * max_n  : W = V^T A  /  max_n * band : W = A U^T
+    void* wpart = nullptr;         // split-K partials
+    size_t wpart_elems = 0;
+    void* s = nullptr;             // band * band   : S (= -T of compact WY), upper triangular
+    void* tau = nullptr;           // band
+    void* red = nullptr;           // panel all-reduce scratch: 2 * kMaxPanelCtas * (2*band + 8)
+    unsigned int* bar = nullptr;   // software grid barrier state (2 words) + misc counters
+    int* prog = nullptr;           // stage-2 per-sweep progress counters (max_n)
+    void* d = nullptr; void* e = nullptr; void* sigma = nullptr;   // max_n each
+    long long* qr_info = nullptr;  // [0] sweeps, [1] status
+    void* tileq = nullptr;         // tile order: per-chain-step Q matrices, (max_n/band) * 4*band*band
+    void* tilestate = nullptr;     // tile order: S_kk,V_kk,... persistent small state
+    // host-side bookkeeping
+    long long launches = 0;
+    cudaEvent_t ev[8] = {};
+    double ms_stage1 = 0, ms_stage2 = 0, ms_qr = 0, ms_h2d = 0, ms_d2h = 0;
+    std::string last_error;
+    int coop_supported = 0;
+};
+
+inline int cuda_status(Ctx* c, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    if (c) {
+        c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    return SVDB200_CUDA_ERR + (int)e;
+}
+
+#define SVDB_CHECK(ctx, expr)                                            \
+    do {                                                                 \
+        cudaError_t _e = (expr);                                         \
+        if (_e != cudaSuccess) return ::svdb200::cuda_status((ctx), _e, #expr); \
+    } while (0)
+#define SVDB_TRY(expr)                 \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != 0) return _s;        \
+    } while (0)
+
+// ---- exactly-rounded, never-contracted arithmetic for the bit-faithful kernels -------------------
+// (the reference is compiled without FMA contraction: ISO C++ mode => -ffp-contract=off)
+template <typename T> struct RN;
+template <> struct RN<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+};
+template <> struct RN<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+};
+
+// Householder scalars exactly as svd_serial.h:194-201: s, u1, 1/u1, tau in double, rounded to T.
+template <typename T>
+__device__ __forceinline__ void householder_scalars(T x0, T norm_x, T& alpha, T& tau) {
+    double s = -copysign(1.0, (double)x0);
+    double u1 = __dsub_rn((double)x0, __dmul_rn(s, (double)norm_x));
+    alpha = (T)__ddiv_rn(1.0, u1);
+    tau = (T)__ddiv_rn(__dmul_rn(-s, u1), (double)norm_x);
+}
+
+// L2-coherent accesses for data exchanged between CTAs inside one launch (bypass the non-coherent L1)
+template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+template <typename T> __device__ __forceinline__ void st_cg(T* p, T v) { __stcg(p, v); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Software grid barrier for cooperative launches (all CTAs co-resident). bar[0] = arrival counter,
+// bar[1] = generation. Monotone generation => no reset race.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsigned& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned target = gen + 1;
+        unsigned prev = atomicAdd(&bar[0], 1u);
+        if (prev == nctas * target - 1) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&bar[1]), "r"(target) : "memory");
+        } else {
+            while (ld_acquire_u(&bar[1]) < target) { __nanosleep(20); }
+        }
+        __threadfence();
+    }
+    gen += 1;
+    __syncthreads();
+}
+
+// ---- internal entry points (one per .cu) ----------------------------------------------------------
+template <typename T> int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e);
+template <typename T> int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma);
+template <typename T> int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band);
+template <typename T> int stage1_tile_order(Ctx* c, T* a, size_t n, size_t band);
+template <typename T> int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, T* w);
+template <typename T> int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* ut, T* w);
+template <typename T> int rank_update(Ctx* c, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* p, const T* q, size_t ldq);
+template <typename T> int fill_uniform(Ctx* c, T* a, size_t count, unsigned long long seed, double lo, double hi);
+template <typename T> int mse_metric(Ctx* c, const T* a, const T* b, size_t n, size_t band, T* out_host);
+template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma);
+int probe_peak(Ctx* c, int kind, double* tflops);
+
+}  // namespace svdb200

@@ -1,0 +1,231 @@
+// Stage 1, panel order: dense -> band by full-height panel QR / full-width panel LQ with a
+// compact-WY trailing update.  Replaces csc586::gpu::cuda_brd_p1 (svd_cuda_1.cu:750,
+// svd_cuda_2.cu:1117) / csc586::gpu::brd_p1 (svd_cpu.h:370) and their helpers qr_cuda/lq_cuda
+// (svd_cuda_2.cu:881/959), hholder_cuda (797), wy_compact_cuda (838).
+//
+// Panel kernel (one cooperative launch per panel instead of ~25 launches per COLUMN):
+//   * the m x b panel is distributed by rows over G CTAs and stays resident in shared memory for
+//     the whole factorisation (an LQ row panel is loaded transposed, so one code path serves both);
+//   * per column ONE grid-wide all-reduce: every CTA publishes the dot products of the pivot
+//     column with all b columns over its rows (warp-shuffle reductions), the pivot-row owner
+//     publishes the pivot row; after the barrier every CTA forms ||x||, the Householder scalars
+//     (sign convention of svd_serial.h:194-201: H x = -sign(x0)||x|| e1), the rank-1 update
+//     coefficients and column j of the compact-WY factor S (= -T, svd_parallel.h:97-113)
+//     redundantly from the reduced vector -- no second synchronisation;
+//   * partial sums are combined in CTA order, so the result is deterministic.
+// Outputs: R (or L) written into A with exact zeros below the diagonal of the panel, V (m x b,
+// unit diagonal explicit), V2 = V S^T, and S.
+#include "common.cuh"
+
+namespace svdb200 {
+namespace {
+
+constexpr int kPanelThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Panel element (r, c): r in [0,m) along the reflector direction, c in [0,b).
+//   kTrans == false (QR): A[r*lda + c]        kTrans == true (LQ): A[c*lda + r]
+template <typename T, bool kTrans>
+__global__ void __launch_bounds__(kPanelThreads)
+panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_cta, T* __restrict__ V, T* __restrict__ V2,
+                    T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int G = gridDim.x, g = blockIdx.x;
+    const int r0 = g * rows_per_cta;
+    const int R = max(0, min(rows_per_cta, m - r0));     // local rows
+    const int ld = b + 1;
+    T* Ps = reinterpret_cast<T*>(smem_raw);              // R x ld
+    T* Ss = Ps + (size_t)rows_per_cta * ld;              // b x b
+    T* zs = Ss + b * b;                                  // b : local partial dots / reduced dots
+    T* piv = zs + b;                                     // b : pivot row
+    T* fs = piv + b;                                     // b : update coefficients
+    T* gs = fs + b;                                      // b : V_k^T v_j
+    T* taus = gs + b;                                    // b
+    unsigned gen = 0;
+
+    // ---- load the local slice --------------------------------------------------------------------
+    if (!kTrans) {
+        for (int e = tid; e < R * b; e += nt) {
+            int rl = e / b, c = e - rl * b;
+            Ps[rl * ld + c] = A[(size_t)(r0 + rl) * lda + c];
+        }
+    } else {
+        for (int e = tid; e < R * b; e += nt) {
+            int c = e / R, rl = e - c * R;
+            Ps[rl * ld + c] = A[(size_t)c * lda + (r0 + rl)];
+        }
+    }
+    for (int e = tid; e < b * b; e += nt) Ss[e] = (T)0;
+    __syncthreads();
+
+    const int kmax = min(b, m);
+    const int slot = 2 * b;                               // per-CTA scratch: b dots + b pivot-row values
+    for (int j = 0; j < kmax; ++j) {
+        T* buf = red + (size_t)(j & 1) * (G + 1) * slot;
+        // ---- phase A: local dots of column j (rows > j) with every column ---------------------------
+        const int lo = max(0, j + 1 - r0);               // first local row with global index > j
+        for (int c = warp; c < b; c += nwarps) {
+            T acc = (T)0;
+            for (int rl = lo + lane; rl < R; rl += 32) acc += Ps[rl * ld + c] * Ps[rl * ld + j];
+            acc = warp_sum(acc);
+            if (lane == 0) st_cg(&buf[(size_t)g * slot + c], acc);
+        }
+        if (j >= r0 && j < r0 + R) {                     // owner of the pivot row publishes it
+            for (int c = tid; c < b; c += nt) st_cg(&buf[(size_t)G * slot + c], Ps[(j - r0) * ld + c]);
+        }
+        grid_barrier(bar, (unsigned)G, gen);
+        // ---- phase B: ordered reduction (deterministic) ----------------------------------------------
+        for (int c = tid; c < b; c += nt) {
+            T acc = (T)0;
+            for (int q = 0; q < G; ++q) acc += ld_cg(&buf[(size_t)q * slot + c]);
+            zs[c] = acc;
+            piv[c] = ld_cg(&buf[(size_t)G * slot + c]);
+        }
+        __syncthreads();
+        // ---- phase C: scalars, S column, rank-1 update --------------------------------------------------
+        const T x0 = piv[j];
+        const T normsq = zs[j] + x0 * x0;
+        const T nrm = sqrt(normsq);
+        const double sgn = -copysign(1.0, (double)x0);
+        const double u1 = (double)x0 - sgn * (double)nrm;
+        const T alpha = (T)(1.0 / u1);
+        const T tau = (T)(-sgn * u1 / (double)nrm);
+        const T beta = (T)(sgn * (double)nrm);           // R_jj = -sign(x0) ||x||
+        for (int c = tid; c < b; c += nt) {
+            if (c > j) {
+                // w^T a_c with w = [1; alpha*x_{>j}] :  piv[c] + alpha * sum_{r>j} x_r a_rc
+                fs[c] = tau * (piv[c] + alpha * zs[c]);
+            } else if (c < j) {
+                // V[:,c]^T v_j = V[j][c] * 1 + alpha * sum_{r>j} V[r][c] x_r
+                gs[c] = piv[c] + alpha * zs[c];
+            }
+        }
+        if (tid == 0) taus[j] = tau;
+        __syncthreads();
+        // S[0:j, j] = -tau * S[0:j,0:j] * g ; S[j][j] = -tau   (svd_parallel.h:102-111)
+        if (tid < j) {
+            T acc = (T)0;
+            for (int c = tid; c < j; ++c) acc += Ss[tid * b + c] * gs[c];   // S upper triangular
+            Ss[tid * b + j] = -tau * acc;
+        } else if (tid == j) {
+            Ss[j * b + j] = -tau;
+        }
+        // scale the pivot column into w (rows > j), store beta on the pivot row
+        for (int rl = lo + tid; rl < R; rl += nt) Ps[rl * ld + j] *= alpha;
+        if (j >= r0 && j < r0 + R && tid == 0) Ps[(j - r0) * ld + j] = beta;
+        __syncthreads();
+        // rows >= j, columns > j :  a_rc -= w_r * f_c
+        const int lo2 = max(0, j - r0);
+        const int ncu = b - j - 1;
+        if (ncu > 0) {
+            for (int e = tid; e < (R - lo2) * ncu; e += nt) {
+                int rl = lo2 + e / ncu, c = j + 1 + e % ncu;
+                T wv = (r0 + rl == j) ? (T)1 : Ps[rl * ld + j];
+                Ps[rl * ld + c] -= wv * fs[c];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: V, V2 = V S^T, S, and the factored panel back into A ---------------------------
+    // V(row, k) = 1 (row == k), Ps (row > k), 0 (row < k)
+    for (int e = tid; e < R * b; e += nt) {
+        int rl = e / b, c = e - rl * b;
+        int row = r0 + rl;
+        T vv = (row == c) ? (T)1 : (row > c ? Ps[rl * ld + c] : (T)0);
+        if (c >= kmax) vv = (T)0;
+        T acc = (T)0;                                     // V2[row][c] = sum_{k >= c} V[row][k] * S[c][k]
+        int khi = min(kmax - 1, row);
+        for (int k = c; k <= khi; ++k) {
+            T vk = (row == k) ? (T)1 : Ps[rl * ld + k];
+            acc += vk * Ss[c * b + k];
+        }
+        V[(size_t)row * b + c] = vv;
+        if (!kTrans) V2[(size_t)row * b + c] = acc;
+        else V2[(size_t)c * m + row] = acc;
+    }
+    if (!kTrans) {
+        for (int e = tid; e < R * b; e += nt) {
+            int rl = e / b, c = e - rl * b;
+            int row = r0 + rl;
+            A[(size_t)row * lda + c] = (c >= row) ? Ps[rl * ld + c] : (T)0;
+        }
+    } else {
+        for (int e = tid; e < R * b; e += nt) {
+            int c = e / R, rl = e - c * R;
+            int row = r0 + rl;
+            A[(size_t)c * lda + row] = (c >= row) ? Ps[rl * ld + c] : (T)0;
+        }
+    }
+    if (g == 0) for (int e = tid; e < b * b; e += nt) S_out[e] = Ss[e];
+}
+
+template <typename T, bool kTrans>
+int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
+    // rows per CTA: at least 64, and no more CTAs than SMs (cooperative launch needs co-residency)
+    int G = (m + 63) / 64;
+    if (G > c->num_sms) G = c->num_sms;
+    if (G > kMaxPanelCtas) G = kMaxPanelCtas;
+    if (G < 1) G = 1;
+    int rows = (m + G - 1) / G;
+    G = (m + rows - 1) / rows;
+    size_t smem = ((size_t)rows * (b + 1) + (size_t)b * b + 5 * (size_t)b + 8) * sizeof(T);
+    if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
+    auto kern = panel_factor_kernel<T, kTrans>;
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), c->stream));
+    T* V = reinterpret_cast<T*>(c->v);
+    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* S = reinterpret_cast<T*>(c->s);
+    T* red = reinterpret_cast<T*>(c->red);
+    unsigned* bar = c->bar;
+    void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar};
+    SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
+}  // namespace
+
+// Driver: same panel sequence as svd_cpu.h:382-423 / svd_cuda_2.cu:1148-1213.
+template <typename T>
+int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
+    if (band == 0 || n == 0 || n % band != 0) return SVDB200_E_SHAPE;
+    if (band > (size_t)kMaxBand || n > c->max_n || band > c->band) return SVDB200_E_CAPACITY;
+    const int b = (int)band;
+    T* V = reinterpret_cast<T*>(c->v);
+    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* W = reinterpret_cast<T*>(c->w);
+    for (size_t k = 0; k < n; k += band) {
+        const size_t m = n - k;                 // panel height
+        const size_t nc = n - k - band;         // columns right of the QR panel
+        SVDB_TRY((launch_panel<T, false>(c, a + k * n + k, n, (int)m, b)));
+        if (nc > 0) {
+            T* A2 = a + k * n + k + band;
+            SVDB_TRY(gemm_tn<T>(c, V, A2, n, m, nc, band, W));                   // W = V^T A2
+            SVDB_TRY(rank_update<T>(c, A2, n, m, nc, band, V2, W, nc));          // A2 += (V S^T) W
+        }
+        if (k + band < n - 1) {
+            const size_t mr = m - band;         // rows below the LQ row panel
+            SVDB_TRY((launch_panel<T, true>(c, a + k * n + k + band, n, (int)nc, b)));
+            if (mr > 0) {
+                T* A3 = a + (k + band) * n + k + band;
+                SVDB_TRY(gemm_nn<T>(c, A3, n, mr, nc, band, V, W));              // W = A3 U^T
+                SVDB_TRY(rank_update<T>(c, A3, n, mr, nc, band, W, V2, nc));     // A3 += W (S U)
+            }
+        }
+    }
+    return 0;
+}
+
+template int stage1_panel_order<float>(Ctx*, float*, size_t, size_t);
+template int stage1_panel_order<double>(Ctx*, double*, size_t, size_t);
+
+}  // namespace svdb200

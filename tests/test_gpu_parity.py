@@ -1,0 +1,252 @@
+"""GPU parity tests (-m gpu): every call goes through the C-ABI (libsvdb200.so via ctypes) and is
+checked against the CPU oracle / the reference's golden vectors.
+
+Bars: bit-exact where the kernel is bit-faithful (stage 2, tile-order stage 1);
+max-abs-diff over the band diagonals / max|ref| <= 1e-10 (double) / 1e-4 (float) otherwise."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, band_rel, load_fixture
+from svdsolver_b200.synth import uniform_matrix
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": np.float32, "f64": np.float64}
+NAME = {"f32": "float", "f64": "double"}
+TOL = {"f32": 1e-4, "f64": 1e-10}
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from svdsolver_b200 import capi as m
+    m.lib()
+    return m
+
+
+def handle(capi, n, band, suf):
+    return capi.Handle(n, band, DT[suf])
+
+
+# ------------------------------------------------------------------ stage 2 (bit-faithful) -------
+@pytest.mark.parametrize("n", [64, 512])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage2_fixture_band_to_bidiagonal_bit_exact(capi, n, suf):
+    """P2: stage 2 alone, input = fixture band bytes, output == fixture bidiagonal bytes."""
+    band = load_fixture("band", NAME[suf], n)
+    ref = load_fixture("bidiagonal", NAME[suf], n)
+    with handle(capi, n, 4, suf) as h:
+        out, d, e = h.band_to_bidiag(band, 4)
+    assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
+    assert np.array_equal(d, np.diagonal(ref)) and np.array_equal(e, np.diagonal(ref, 1))
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage2_regenerated_1024_bit_exact(capi, oracle, suf):
+    g = np.load(os.path.join(GOLDEN, "golden_1024.npz"))
+    a = uniform_matrix(1024, 1024, 586 + 1024, 1.0, 5.0, DT[suf])
+    band = oracle.brd_p1(a, 4)
+    ref, d_ref, e_ref = oracle.brd_p2(band, 4)
+    assert np.array_equal(d_ref, g[f"bidiag_d_{suf}"])       # oracle pinned to the compiled reference
+    with handle(capi, 1024, 4, suf) as h:
+        out, d, e = h.band_to_bidiag(band, 4)
+    assert np.array_equal(out, ref) and np.array_equal(d, d_ref) and np.array_equal(e, e_ref)
+
+
+@pytest.mark.parametrize("n,b", [(96, 32), (128, 16), (64, 8), (192, 32), (256, 64), (40, 4), (32, 32)])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage2_other_bands_bit_exact(capi, n, b, suf):
+    g = np.load(os.path.join(GOLDEN, "golden_random.npz"))
+    with handle(capi, n, b, suf) as h:
+        out, _, _ = h.band_to_bidiag(g[f"band_{n}_{b}_{suf}"], b)
+    assert np.array_equal(out, g[f"bidiag_{n}_{b}_{suf}"])
+
+
+@pytest.mark.parametrize("n,b", [(65, 4), (67, 4), (100, 7), (33, 32), (2, 1), (3, 2)])
+def test_stage2_ragged_sizes_vs_oracle(capi, oracle, n, b):
+    """n not a multiple of the band, tiny matrices: clamped / degenerate windows (SURVEY 8a'')."""
+    a = np.triu(np.tril(uniform_matrix(n, n, 5 + n, 1.0, 5.0, np.float64), b))
+    ref, d_ref, e_ref = oracle.brd_p2(a, b)
+    with handle(capi, n, b, "f64") as h:
+        out, d, e = h.band_to_bidiag(a, b)
+    assert np.array_equal(out, ref)
+
+
+# ------------------------------------------------------------------ stage 1, tile order -----------
+@pytest.mark.parametrize("n", [64, 512])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage1_tile_order_fixture_bit_exact(capi, n, suf):
+    """P1 (signed): dense fixture -> band fixture, every byte."""
+    a = load_fixture("test", NAME[suf], n)
+    ref = load_fixture("band", NAME[suf], n)
+    with handle(capi, n, 4, suf) as h:
+        out = h.dense_to_band(a, 4, capi.ORDER_TILE)
+    assert band_rel(out, ref, 4) <= TOL[suf]
+    assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.parametrize("n,b", [(96, 32), (128, 16), (64, 8), (192, 32), (256, 64), (40, 4), (32, 32)])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage1_tile_order_other_bands_bit_exact(capi, n, b, suf):
+    g = np.load(os.path.join(GOLDEN, "golden_random.npz"))
+    a = uniform_matrix(n, n, 586 + n + b, 0.0, 5.0, DT[suf])
+    with handle(capi, n, b, suf) as h:
+        out = h.dense_to_band(a, b, capi.ORDER_TILE)
+    assert np.array_equal(out, g[f"band_{n}_{b}_{suf}"])
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_chain_tile_order_1024_matches_reference_digest(capi, suf):
+    """BASELINE config 1 shape (1024, band 4): GPU chain == compiled reference, via its digests."""
+    import hashlib
+    meta = json.load(open(os.path.join(GOLDEN, "golden_meta.json")))[f"1024_{suf}"]
+    a = uniform_matrix(1024, 1024, 586 + 1024, 1.0, 5.0, DT[suf])
+    sha = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
+    with handle(capi, 1024, 4, suf) as h:
+        band = h.dense_to_band(a, 4, capi.ORDER_TILE)
+        assert sha(band) == meta["band_sha256"]
+        bid, _, _ = h.band_to_bidiag(band, 4)
+        assert sha(bid) == meta["bidiagonal_sha256"]
+
+
+# ------------------------------------------------------------------ stage 1, panel order ----------
+@pytest.mark.parametrize("n,b", [(64, 4), (96, 32), (128, 16), (256, 32), (256, 64), (320, 32)])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage1_panel_order_vs_oracle(capi, oracle, n, b, suf):
+    """Signed parity with the reference's panel algorithm (gpu::brd_p1 / cuda_brd_p1 order)."""
+    a = uniform_matrix(n, n, 586 + n + b, 0.0, 5.0, DT[suf])
+    ref = oracle.brd_p1_panel(a, b)
+    with handle(capi, n, b, suf) as h:
+        out = h.dense_to_band(a, b, capi.ORDER_PANEL)
+    assert band_rel(out, ref, b) <= TOL[suf]
+    # band structure: exact zeros below the diagonal, round-off above the band
+    assert np.abs(np.tril(out, -1)).max() == 0
+    assert np.abs(np.triu(out, b + 1)).max() <= (1e-4 if suf == "f32" else 1e-12) * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [64, 512])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage1_panel_order_vs_fixture_up_to_signs(capi, n, suf):
+    """The reference's own `check` semantics: |.|-insensitive comparison with band_* (mse)."""
+    a = load_fixture("test", NAME[suf], n)
+    ref = load_fixture("band", NAME[suf], n)
+    with handle(capi, n, 4, suf) as h:
+        out = h.dense_to_band(a, 4, capi.ORDER_PANEL)
+        mse = h.mse(out, ref, 4)
+    assert band_rel(np.abs(out), np.abs(ref), 4) <= TOL[suf]
+    assert mse <= TOL[suf] * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_stage1_panel_order_invariants_2048(capi, suf):
+    """Size the oracle cannot reach in seconds: band structure, Frobenius norm, singular values."""
+    n, b = 2048, 32
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    with handle(capi, n, b, suf) as h:
+        out = h.dense_to_band(a, b, capi.ORDER_PANEL).astype(np.float64)
+    tol = TOL[suf]
+    assert np.abs(np.tril(out, -1)).max() == 0
+    assert np.abs(np.triu(out, b + 1)).max() <= tol * np.abs(out).max()
+    fa = np.linalg.norm(a.astype(np.float64))
+    assert abs(np.linalg.norm(out) - fa) <= tol * fa
+    s0 = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+    s1 = np.linalg.svd(np.triu(np.tril(out, b)), compute_uv=False)
+    assert np.abs(s0 - s1).max() <= tol * s0[0]
+
+
+# ------------------------------------------------------------------ trailing-update GEMMs ---------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("m,n,b", [(256, 192, 32), (300, 130, 64), (64, 60, 4), (1000, 777, 16)])
+def test_trailing_update_gemms(capi, suf, m, n, b):
+    import torch
+    dt = torch.float32 if suf == "f32" else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ld = n + 8
+    C = torch.rand(m, ld, device="cuda", dtype=dt, generator=g)
+    V = torch.rand(m, b, device="cuda", dtype=dt, generator=g) - 0.5
+    Ut = torch.rand(n, b, device="cuda", dtype=dt, generator=g) - 0.5
+    Q = torch.rand(b, n, device="cuda", dtype=dt, generator=g) - 0.5
+    tol = 2e-5 if suf == "f32" else 1e-12
+    with handle(capi, max(m, n) + 64, b, suf) as h:
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        W = torch.empty(b, n, device="cuda", dtype=dt)
+        h.gemm_tn_dev(V.data_ptr(), C.data_ptr(), ld, m, n, b, W.data_ptr())
+        ref = (V.double().T @ C[:, :n].double())
+        assert (W.double() - ref).abs().max().item() <= tol * ref.abs().max().item()
+        W2 = torch.empty(m, b, device="cuda", dtype=dt)
+        h.gemm_nn_dev(C.data_ptr(), ld, m, n, b, Ut.data_ptr(), W2.data_ptr())
+        ref2 = C[:, :n].double() @ Ut.double()
+        assert (W2.double() - ref2).abs().max().item() <= tol * ref2.abs().max().item()
+        C2 = C.clone()
+        h.rank_update_dev(C2.data_ptr(), ld, m, n, b, V.data_ptr(), Q.data_ptr(), n)
+        ref3 = C[:, :n].double() + V.double() @ Q.double()
+        torch.cuda.synchronize()
+        assert (C2[:, :n].double() - ref3).abs().max().item() <= tol * ref3.abs().max().item()
+        assert torch.equal(C2[:, n:], C[:, n:])          # padding columns untouched
+
+
+# ------------------------------------------------------------------ QR diagonalisation -------------
+@pytest.mark.parametrize("n", [8, 64, 320, 640])
+def test_bidiag_qr_float_vs_reference_qrd(capi, n):
+    g = np.load(os.path.join(GOLDEN, "golden_qrd.npz"))
+    de = uniform_matrix(2, n, 586 + n, 0.0, 5.0, np.float32)
+    with handle(capi, n, 1, "f32") as h:
+        sigma, sweeps = h.bidiag_qr(de[0], de[1, : n - 1])
+    ref = g[f"qrd_sigma_{n}"]
+    assert sweeps > 0
+    assert np.abs(sigma - ref).max() <= 1e-4 * ref[0]
+
+
+@pytest.mark.parametrize("n", [64, 512])
+def test_bidiag_qr_on_fixture_bidiagonal(capi, n):
+    g = np.load(os.path.join(GOLDEN, "golden_qrd.npz"))
+    m = load_fixture("bidiagonal", "float", n)
+    with handle(capi, n, 1, "f32") as h:
+        sigma, _ = h.bidiag_qr(np.diagonal(m).copy(), np.diagonal(m, 1).copy())
+    ref = g[f"qrd_sigma_fixture_{n}"]
+    assert np.abs(sigma - ref).max() <= 1e-4 * ref[0]
+
+
+@pytest.mark.parametrize("n", [2, 3, 100, 1000])
+def test_bidiag_qr_double_vs_lapack(capi, n):
+    de = uniform_matrix(2, n, 99 + n, 0.0, 5.0, np.float64)
+    d, e = de[0].copy(), de[1, : n - 1].copy()
+    with handle(capi, n, 1, "f64") as h:
+        sigma, _ = h.bidiag_qr(d, e)
+    ref = np.linalg.svd(np.diag(d) + np.diag(e, 1), compute_uv=False)
+    assert np.all(np.diff(sigma) <= 0)
+    assert np.abs(sigma - ref).max() <= 1e-10 * ref[0]
+
+
+# ------------------------------------------------------------------ full chain ---------------------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_svdvals_chain_tile_order_vs_oracle_sigma(capi, oracle, suf):
+    """P3: sigma of the GPU chain vs sigma of the oracle's bidiagonal (float: qrd<float>; double: LAPACK)."""
+    n, b = 256, 8
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    bid, d, e = oracle.brd_p2(oracle.brd_p1(a, b), b)
+    with handle(capi, n, b, suf) as h:
+        sigma, a_out = h.svdvals(a, b, capi.ORDER_TILE)
+    assert np.array_equal(a_out, bid)
+    if suf == "f32":
+        ref, _, sweeps, _, _ = oracle.qrd(d, e)
+        assert sweeps >= 0
+    else:
+        ref = np.linalg.svd(np.diag(d) + np.diag(e, 1), compute_uv=False)
+    assert np.abs(sigma - ref).max() <= TOL[suf] * ref[0]
+
+
+def test_error_statuses(capi):
+    a = np.zeros((10, 10))
+    with handle(capi, 64, 4, "f64") as h:
+        with pytest.raises(capi.SvdB200Error) as ei:
+            h.dense_to_band(a, 4)               # 10 % 4 != 0  (matrix.h:407 needs t | n)
+        assert ei.value.status == -2
+        with pytest.raises(capi.SvdB200Error) as ei:
+            h.dense_to_band(np.zeros((128, 128)), 4)
+        assert ei.value.status == -3
+        with pytest.raises(capi.SvdB200Error) as ei:
+            h.dense_to_band(np.zeros((8, 12)), 4)
+        assert ei.value.status == -2
