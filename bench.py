@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the SVDSolver hot path on B200 (BASELINE.json metric: bidiagonal-reduction GFLOP/s).
+
+Workload (BASELINE.json configs[1], the reference's own benchmark shape `benchmark 320 12 1 32`,
+svd_cuda_2.cu:1365-1371): square matrices n = 320..3840 step 320, band 32, U[0,5) synthetic inputs
+(svdsolver_b200/synth.py), in double AND float.  One "step" = the full dense -> band -> bidiagonal
+reduction (stage 1 panel order + stage 2) of all 24 matrices.  Algorithmic work = 8 n^3 / 3 flops
+per matrix, value = total flops / device time.
+
+  value     inputs resident in HBM before the timed region; CUDA events on the launching stream,
+            max over ranks; every step works on a fresh copy set (0.8 GB/step > 126 MB L2).
+  e2e       the same reduction through the host-pointer C-ABI call svdb200_bidiagonalize_* with
+            pinned HOST buffers: H2D of the matrix and D2H of matrix + d + e inside the timed region.
+  roofline  the stage-1 rank-b trailing update (C += P Q, the dominant kernel), timed per launch
+            with CUDA events in an extra profiled pass over the same workload, against the FP64
+            DMMA (mma.sync) peak measured in the same run by a register-resident probe.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/libsvdref_fast.so = parallel::brd_p1 + brd_p2
+            built from /root/reference with the README's -O3 -mavx) on the host cores, bounded sample.
+
+`--impl reference` times the reference's CPU implementation alone (rank 0 only) on the same metric.
+Multi-GPU (torchrun, one rank per GPU): the matrices of the sweep are independent, so each rank
+reduces its own replica of the sweep (weak scaling, no data-path collective).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BAND = 32
+SIZES = [320 * k for k in range(1, 13)]
+DTYPES = (("f64", np.float64), ("f32", np.float32))
+METRIC = "bidiag_reduction_gflops"
+UNIT = "GFLOP/s"
+
+
+def flops(n):
+    return 8.0 * n ** 3 / 3.0
+
+
+def workload_config(extra=None):
+    cfg = {
+        "workload": "reference sweep n=320..3840 step 320, band 32, float and double, dense->band->bidiagonal "
+                    "(BASELINE configs[1]); 24 matrices per step",
+        "band": BAND, "sizes": SIZES, "dtypes": ["f64", "f32"], "stage1_order": "panel",
+        "inputs": "U[0,5) splitmix64 stream, seed 586+n", "l2": "fresh 0.8 GB input copy set per step (> 126 MB L2)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------ CPU reference leg
+def load_reference():
+    fast = os.path.join(ROOT, "oracle", "_ref", "libsvdref_fast.so")
+    if os.path.exists(fast):
+        return ctypes.CDLL(fast), "reference"
+    # fall back to the C restatement (kind "port") -- still the checker, never the product
+    port = os.path.join(ROOT, "oracle", "libsvd_oracle.so")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), port])
+    return ctypes.CDLL(port), "port"
+
+
+def cpu_reference_sample(sizes):
+    """Times parallel::brd_p1 + parallel::brd_p2 (chained) on the host for the given sizes, f64+f32."""
+    from svdsolver_b200.synth import uniform_matrix
+    lib, kind = load_reference()
+    tot_t, tot_f, detail = 0.0, 0.0, []
+    for n in sizes:
+        for suf, dt in DTYPES:
+            a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt)
+            t1, t2 = ctypes.c_double(0), ctypes.c_double(0)
+            if kind == "reference":
+                getattr(lib, f"svdref_time_multicore_{suf}")(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.c_size_t(BAND),
+                                                             ctypes.c_int(1), ctypes.byref(t1), ctypes.byref(t2))
+                dt_s = t1.value + t2.value
+            else:
+                x = a.copy()
+                t0 = time.perf_counter()
+                getattr(lib, f"svdo_brd_p1_{suf}")(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.c_size_t(BAND))
+                getattr(lib, f"svdo_brd_p2_{suf}")(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.c_size_t(BAND), None, None)
+                dt_s = time.perf_counter() - t0
+            tot_t += dt_s
+            tot_f += flops(n)
+            detail.append({"n": n, "dtype": suf, "seconds": round(dt_s, 4)})
+    cores = lib.svdref_omp_threads() if kind == "reference" else (os.cpu_count() or 1)
+    return {"value": tot_f / tot_t * 1e-9, "unit": UNIT, "cores": int(cores), "kind": kind,
+            "sample": f"n={sizes} band {BAND} f64+f32, stage1+stage2 chained, timing.h:78-83 timer convention", "seconds": round(tot_t, 3),
+            "detail": detail}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    per_step_sizes = [320, 640] if (args.steps + args.warmup) * 15.0 <= 160.0 else [320]
+    for _ in range(args.warmup):
+        cpu_reference_sample(per_step_sizes[:1])
+    t0 = time.perf_counter()
+    last = None
+    tot_f = 0.0
+    for _ in range(args.steps):
+        last = cpu_reference_sample(per_step_sizes)
+        tot_f += sum(flops(n) for n in per_step_sizes) * len(DTYPES)
+    dt = time.perf_counter() - t0
+    value = tot_f / dt * 1e-9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64,f32", "data": "synthetic",
+        "config": workload_config({"sample": f"bounded: n={per_step_sizes} of the sweep per step (the full sweep takes ~45 min on 8 cores, BASELINE.md 2b)"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="svdb200")
+    ap.add_argument("--sizes", default="")           # debugging: comma-separated subset of the sweep
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else SIZES
+
+    import torch
+    import torch.distributed as dist
+    from svdsolver_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    nmax = max(sizes)
+    handles = {suf: capi.Handle(nmax, BAND, dt, device=local_rank) for suf, dt in DTYPES}
+    for h in handles.values():
+        h.set_stream(stream.cuda_stream)
+    tdt = {"f64": torch.float64, "f32": torch.float32}
+
+    nsets = args.steps + args.warmup
+    free_b, _ = torch.cuda.mem_get_info()
+    set_bytes = sum(n * n for n in sizes) * 12
+    nsets = max(1, min(nsets, int(free_b * 0.7 // set_bytes)))
+    sets = []
+    for s in range(nsets):
+        cur = []
+        for n in sizes:
+            for suf, _ in DTYPES:
+                a = torch.empty(n, n, device=dev, dtype=tdt[suf])
+                handles[suf].fill_uniform_dev(a.data_ptr(), n * n, 586 + n, 0.0, 5.0)
+                cur.append((n, suf, a))
+        sets.append(cur)
+    dbuf = {suf: torch.empty(nmax, device=dev, dtype=tdt[suf]) for suf, _ in DTYPES}
+    ebuf = {suf: torch.empty(nmax, device=dev, dtype=tdt[suf]) for suf, _ in DTYPES}
+
+    def refill(cur):
+        for n, suf, a in cur:
+            handles[suf].fill_uniform_dev(a.data_ptr(), n * n, 586 + n, 0.0, 5.0)
+
+    def step(cur):
+        for n, suf, a in cur:
+            handles[suf].bidiagonalize_dev(a.data_ptr(), n, BAND, dbuf[suf].data_ptr(), ebuf[suf].data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for w in range(args.warmup):
+        step(sets[w % nsets])
+    torch.cuda.synchronize()
+    reused = nsets < args.steps + args.warmup
+    if reused:
+        for cur in sets:
+            refill(cur)
+    # ---- timed region: EXACTLY `steps` steps ----------------------------------------------------
+    launches0 = sum(h.launch_count() for h in handles.values())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.steps):
+        idx = (args.warmup + s) % nsets
+        if reused and s >= nsets:
+            refill(sets[idx])
+        step(sets[idx])
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(h.launch_count() for h in handles.values()) - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    step_flops = sum(flops(n) for n in sizes) * len(DTYPES)
+    value = world * step_flops * args.steps / (ms * 1e-3) * 1e-9
+
+    # ---- per-size / per-dtype breakdown (device time, one extra untimed-for-`value` pass) --------
+    detail = []
+    if rank == 0:
+        cur = sets[0]
+        refill(cur)
+        torch.cuda.synchronize()
+        for n, suf, a in cur:
+            h = handles[suf]
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            h.dense_to_band_dev(a.data_ptr(), n, BAND)
+            e1.record(stream)
+            h.band_to_bidiag_dev(a.data_ptr(), n, BAND, dbuf[suf].data_ptr(), ebuf[suf].data_ptr())
+            e2.record(stream)
+            torch.cuda.synchronize()
+            t1, t2 = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            detail.append({"n": n, "dtype": suf, "stage1_ms": round(t1, 3), "stage2_ms": round(t2, 3),
+                           "gflops": round(flops(n) / ((t1 + t2) * 1e-3) * 1e-9, 1),
+                           "stage1_gflops": round(flops(n) / (t1 * 1e-3) * 1e-9, 1)})
+
+    # ---- roofline of the dominant kernel: profiled pass, CUDA events per launch ------------------
+    roofline, prof_out, peaks = None, None, {}
+    if rank == 0:
+        h = handles["f64"]
+        peaks = {"dfma_tflops": h.probe_peak(0), "dmma_f64_tflops": h.probe_peak(1), "ffma_tflops": h.probe_peak(2),
+                 "tf32_mma_sync_tflops": h.probe_peak(3)}
+        cur = sets[0]
+        refill(cur)
+        torch.cuda.synchronize()
+        h.reset_profile()
+        h.set_profile(True)
+        for n, suf, a in cur:
+            if suf == "f64":
+                h.bidiagonalize_dev(a.data_ptr(), n, BAND, dbuf[suf].data_ptr(), ebuf[suf].data_ptr())
+        torch.cuda.synchronize()
+        h.set_profile(False)
+        prof = h.get_profile()
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        prof_out = {k: {"ms": round(v["ms"], 3), "launches": v["launches"], "share": round(v["ms"] / tot_ms, 3),
+                        "achieved": (round(v["work"] / (v["ms"] * 1e-3) * 1e-12, 3) if v["ms"] > 0 and k not in ("stage2", "qr") else
+                                     (round(v["work"] / (v["ms"] * 1e-3) * 1e-9, 2) if v["ms"] > 0 and k == "stage2" else None)),
+                        "unit": "TFLOP/s" if k not in ("stage2", "qr") else ("GB/s window traffic" if k == "stage2" else None)}
+                    for k, v in prof.items()}
+        ru = prof["rank_update"]
+        ach = ru["work"] / (ru["ms"] * 1e-3) * 1e-12 if ru["ms"] > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "rank_update_kernel<double> (C += P Q, K = band)", "achieved": round(ach, 3),
+                    "peak": round(peaks["dmma_f64_tflops"], 2), "unit": "TFLOP/s", "frac": round(ach / peaks["dmma_f64_tflops"], 4),
+                    "traffic": None,
+                    "peak_source": "FP64 DMMA mma.sync.m8n8k4 register-resident probe measured in this run "
+                                   "(MEASURED_PEAKS.json holds only HBM copy and bf16 cuBLAS peaks)",
+                    "launches_timed": ru["launches"], "avg_launch_us": round(ru["ms"] / max(ru["launches"], 1) * 1e3, 2)}
+
+    # ---- e2e: host-pointer C-ABI call with pinned host buffers --------------------------------------
+    from svdsolver_b200.synth import uniform_matrix
+    e2e = None
+    e2e_steps = max(1, min(args.steps, 3))
+    host = []
+    h2d = d2h = 0
+    for n in sizes:
+        for suf, dt in DTYPES:
+            src = torch.from_numpy(uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt))
+            buf = torch.empty(n, n, dtype=tdt[suf]).pin_memory()
+            dh = torch.empty(n, dtype=tdt[suf]).pin_memory()
+            eh = torch.empty(n, dtype=tdt[suf]).pin_memory()
+            host.append((n, suf, src, buf, dh, eh))
+            h2d += n * n * src.element_size()
+            d2h += (n * n + 2 * n - 1) * src.element_size()
+    tot_ms = 0.0
+    for s in range(1 + e2e_steps):
+        for _, _, src, buf, _, _ in host:
+            buf.copy_(src)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for n, suf, _, buf, dh, eh in host:
+            handles[suf].bidiagonalize_inplace(buf.data_ptr(), n, BAND, dh.data_ptr(), eh.data_ptr())
+        a1.record(stream)
+        torch.cuda.synchronize()
+        if s > 0:
+            tot_ms += a0.elapsed_time(a1)
+    if world > 1:
+        t = torch.tensor([tot_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = float(t.item())
+    e2e = {"value": world * step_flops * e2e_steps / (tot_ms * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "svdb200_bidiagonalize_{f64,f32} (host pointers, pinned)"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample([320, 640])
+        cpu.pop("detail", None)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_classes_f64": prof_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
+        }
+        print(json.dumps(line), flush=True)
+    for h in handles.values():
+        h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

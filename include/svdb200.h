@@ -95,6 +95,14 @@ int svdb200_bidiag_qr_f64(svdb200_handle h, const double* d, const double* e, si
 int svdb200_bidiag_qr_dev_f32(svdb200_handle h, float* d_dev, float* e_dev, size_t n, float* sigma_dev);
 int svdb200_bidiag_qr_dev_f64(svdb200_handle h, double* d_dev, double* e_dev, size_t n, double* sigma_dev);
 
+/* ---- Bidiagonal reduction in one call: stage 1 then stage 2 (the two benchmark legs of
+ * `svd_cpu multicore`, svd_cpu.cpp:234-238, chained on the same matrix).  `a` is overwritten by
+ * the bidiagonalised matrix; d (n), e (n-1) receive the bidiagonal. */
+int svdb200_bidiagonalize_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, int order, float* d, float* e);
+int svdb200_bidiagonalize_f64(svdb200_handle h, double* a, size_t m, size_t n, size_t band, int order, double* d, double* e);
+int svdb200_bidiagonalize_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, int order, float* d_dev, float* e_dev);
+int svdb200_bidiagonalize_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, int order, double* d_dev, double* e_dev);
+
 /* ---- Fused chain: singular values of a dense matrix ------------------------------
  * dense -> brd_p1 -> brd_p2 -> qrd.  `a` is overwritten by the bidiagonalised matrix. */
 int svdb200_svdvals_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, int order, float* sigma);
@@ -114,6 +122,16 @@ int svdb200_svdvals_batched_dev_f64(svdb200_handle h, double* a_dev, size_t coun
  * Device time (CUDA events on the handle's stream) of the stages of the LAST host-pointer call, ms.
  * stage-1 sub-times: panel factorisations vs trailing updates are reported by svdb200_stage1_profile. */
 int svdb200_last_timings(svdb200_handle h, double* ms_stage1, double* ms_stage2, double* ms_qr, double* ms_h2d, double* ms_d2h);
+/* Per-kernel-class profiling.  When on, every launch of the hot-path kernels is bracketed by CUDA
+ * events on the handle's stream and its duration and ALGORITHMIC work are accumulated per class:
+ *   0 panel factorisation   (flops 2*m*b^2)            3 rank-b update C += P Q  (flops 2*M*N*b)
+ *   1 W = V^T C             (flops 2*M*N*b)            4 stage-2 bulge chasing   (bytes 4*b*n^2*sizeof(T))
+ *   2 W = C U^T             (flops 2*M*N*b)            5 QR diagonalisation      (n*sweeps steps)
+ * get: arrays of SVDB200_PROFILE_CLASSES entries (ms, work, launches); reset clears them. */
+#define SVDB200_PROFILE_CLASSES 6
+int svdb200_set_profile(svdb200_handle h, int on);
+int svdb200_get_profile(svdb200_handle h, double* ms, double* work, long long* launches);
+int svdb200_reset_profile(svdb200_handle h);
 /* Number of kernel launches issued by this handle since creation (the bench's gpu_launches). */
 long long svdb200_launch_count(svdb200_handle h);
 /* reference error metric gpu::Matrix<T>::mse (matrix_gpu.h:438-453), evaluated on the device. */

@@ -126,6 +126,34 @@ class Handle:
         self._check(self._fn("bidiag_qr")(self.h, _p(d), _p(e), Z(d.shape[0]), _p(sigma), ctypes.byref(sweeps)))
         return sigma, int(sweeps.value)
 
+    def bidiagonalize(self, a, band, order=ORDER_PANEL):
+        a = self._mat(a)
+        n = a.shape[1]
+        d = np.zeros(n, self.dtype)
+        e = np.zeros(max(n - 1, 0), self.dtype)
+        self._check(self._fn("bidiagonalize")(self.h, _p(a), Z(a.shape[0]), Z(n), Z(band), ctypes.c_int(order), _p(d), _p(e)))
+        return a, d, e
+
+    def bidiagonalize_inplace(self, a_ptr, n, band, d_ptr, e_ptr, order=ORDER_PANEL):
+        """Host-pointer call on caller-owned (e.g. pinned) buffers given as raw addresses."""
+        self._check(self._fn("bidiagonalize")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order), _p(d_ptr), _p(e_ptr)))
+
+    def bidiagonalize_dev(self, a_ptr, n, band, d_ptr, e_ptr, order=ORDER_PANEL):
+        self._check(self._fn("bidiagonalize_dev")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order), _p(d_ptr), _p(e_ptr)))
+
+    def set_profile(self, on):
+        self._check(lib().svdb200_set_profile(self.h, ctypes.c_int(1 if on else 0)))
+
+    def reset_profile(self):
+        self._check(lib().svdb200_reset_profile(self.h))
+
+    PROFILE_CLASSES = ("panel", "gemm_tn", "gemm_nn", "rank_update", "stage2", "qr")
+
+    def get_profile(self):
+        ms = (ctypes.c_double * 6)(); work = (ctypes.c_double * 6)(); ln = (ctypes.c_longlong * 6)()
+        self._check(lib().svdb200_get_profile(self.h, ms, work, ln))
+        return {k: {"ms": ms[i], "work": work[i], "launches": int(ln[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def svdvals(self, a, band, order=ORDER_PANEL):
         a = self._mat(a)
         sigma = np.zeros(a.shape[1], self.dtype)

@@ -70,7 +70,10 @@ bidiag_qr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict_
     unsigned long long max_iter = (500ull * (unsigned long long)n) ^ 2ull;   // svd_serial.h:164 ('^' is XOR)
     if (tid == 0) {
         // Criteria<T>::init (svd_serial.h:146-166); sigma[] doubles as scratch for lambda.
-        T eps = (T)1e-8, umin = (T)1e-10, tol = (T)100 * eps;
+        // float: the reference's constants (eps 1e-8, umin 1e-10).  double: the reference does not
+        // compile for double; its float-calibrated constants would cap the accuracy near 1e-7*sigma_1,
+        // above the 1e-10 bar, so the double instantiation scales them (eps 1e-16, umin 1e-20).
+        T eps = sizeof(T) == 4 ? (T)1e-8 : (T)1e-16, umin = sizeof(T) == 4 ? (T)1e-10 : (T)1e-20, tol = (T)100 * eps;
         T lam = RN<T>::abs(d[n - 1]), lmin = lam;
         for (int j = n - 2; j >= 0; --j) {
             lam = RN<T>::abs(d[j]) * lam / (lam + RN<T>::abs(e[j]));
@@ -154,6 +157,7 @@ template <typename T>
 int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma) {
     if (n < 2) return SVDB200_E_SHAPE;
     if (n > c->max_n) return SVDB200_E_CAPACITY;
+    ProfScope ps(c, 5, (double)n);
     int npad = 1;
     while ((size_t)npad < n) npad <<= 1;
     // sort buffer: reuse the stage-2 progress array region is int-sized; use wpart (>= 2*max_n elems)

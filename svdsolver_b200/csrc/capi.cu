@@ -325,6 +325,7 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     SVDB_CREATE_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto& e : c->ev) SVDB_CREATE_CHECK(cudaEventCreate(&e));
+    for (auto& e : c->pev) SVDB_CREATE_CHECK(cudaEventCreate(&e));
     const size_t es = c->esz, nb = round_up(max_n, 128) + 128;
     SVDB_CREATE_CHECK(cudaMalloc(&c->a_dev, es * max_n * max_n));
     SVDB_CREATE_CHECK(cudaMalloc(&c->v, es * nb * band));
@@ -360,6 +361,7 @@ int svdb200_destroy(svdb200_handle h) {
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->pev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -424,6 +426,19 @@ int svdb200_synchronize(svdb200_handle h) {
         if (!d || !e || !sigma) return SVDB200_E_ARG;                                                                    \
         if (n < 2) return SVDB200_E_SHAPE;                                                                               \
         return bidiag_qr<T>(c, d, e, n, sigma);                                                                          \
+    }                                                                                                                    \
+    int svdb200_bidiagonalize_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* d, T* e) {      \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        return host_chain<T>(c, a, n, band, order, 3, d, e, nullptr, nullptr);                                           \
+    }                                                                                                                    \
+    int svdb200_bidiagonalize_dev_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* d, T* e) {  \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
+        SVDB_TRY(stage1_dispatch<T>(c, a, n, band, order));                                                              \
+        return stage2_chase<T>(c, a, n, band, d, e);                                                                     \
     }                                                                                                                    \
     int svdb200_svdvals_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* sigma) {              \
         SVDB_ENTER(T)                                                                                                    \
@@ -510,6 +525,28 @@ int svdb200_last_timings(svdb200_handle h, double* s1, double* s2, double* qr, d
     if (qr) *qr = c->ms_qr;
     if (h2d) *h2d = c->ms_h2d;
     if (d2h) *d2h = c->ms_d2h;
+    return 0;
+}
+
+int svdb200_set_profile(svdb200_handle h, int on) {
+    if (!h) return SVDB200_E_ARG;
+    reinterpret_cast<Ctx*>(h)->profile = on ? 1 : 0;
+    return 0;
+}
+int svdb200_reset_profile(svdb200_handle h) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    for (int i = 0; i < SVDB200_PROFILE_CLASSES; ++i) { c->prof_ms[i] = 0; c->prof_work[i] = 0; c->prof_launches[i] = 0; }
+    return 0;
+}
+int svdb200_get_profile(svdb200_handle h, double* ms, double* work, long long* launches) {
+    if (!h) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    for (int i = 0; i < SVDB200_PROFILE_CLASSES; ++i) {
+        if (ms) ms[i] = c->prof_ms[i];
+        if (work) work[i] = c->prof_work[i];
+        if (launches) launches[i] = c->prof_launches[i];
+    }
     return 0;
 }
 

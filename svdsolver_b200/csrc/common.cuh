@@ -41,6 +41,29 @@ struct Ctx {
     double ms_stage1 = 0, ms_stage2 = 0, ms_qr = 0, ms_h2d = 0, ms_d2h = 0;
     std::string last_error;
     int coop_supported = 0;
+    // per-kernel-class profiling (svdb200_set_profile)
+    int profile = 0;
+    double prof_ms[SVDB200_PROFILE_CLASSES] = {};
+    double prof_work[SVDB200_PROFILE_CLASSES] = {};
+    long long prof_launches[SVDB200_PROFILE_CLASSES] = {};
+    cudaEvent_t pev[2] = {};
+};
+
+// Brackets one kernel launch with events when profiling is on (serialises host and device; the
+// kernel's own duration is unaffected).
+struct ProfScope {
+    Ctx* c; int cls; double work;
+    ProfScope(Ctx* c_, int cls_, double work_) : c(c_), cls(cls_), work(work_) {
+        if (c->profile) cudaEventRecord(c->pev[0], c->stream);
+    }
+    ~ProfScope() {
+        if (!c->profile) return;
+        cudaEventRecord(c->pev[1], c->stream);
+        cudaEventSynchronize(c->pev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->pev[0], c->pev[1]);
+        c->prof_ms[cls] += ms; c->prof_work[cls] += work; c->prof_launches[cls] += 1;
+    }
 };
 
 inline int cuda_status(Ctx* c, cudaError_t e, const char* what) {

@@ -278,6 +278,7 @@ template <typename T>
 int rank_update(Ctx* c, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* p, const T* q, size_t ldq) {
     if (mrows == 0 || ncols == 0) return 0;
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
+    ProfScope ps(c, 3, 2.0 * (double)mrows * (double)ncols * (double)b);
     return launch_rank_update<T, 4, 4>(c, cm, ldc, (int)mrows, (int)ncols, (int)b, p, q, ldq);
 }
 
@@ -286,6 +287,7 @@ int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t nc
     if (mrows == 0 || ncols == 0) return 0;
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
+    ProfScope ps(c, 1, 2.0 * (double)mrows * (double)ncols * (double)b);
     int wm, wn;
     if (B <= 32) { wm = 1; wn = 8; } else if (B <= 64) { wm = 2; wn = 4; } else { wm = 4; wn = 2; }
     const int BMT = wm * 32, BN = wn * 16;
@@ -320,6 +322,7 @@ int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t 
     if (mrows == 0 || ncols == 0) return 0;
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
+    ProfScope ps(c, 2, 2.0 * (double)mrows * (double)ncols * (double)b);
     int wm, wn;
     if (B <= 16) { wm = 8; wn = 1; } else if (B <= 32) { wm = 4; wn = 2; } else if (B <= 64) { wm = 2; wn = 4; } else { wm = 1; wn = 8; }
     const int BM = wm * 32, BNB = wn * 16;

@@ -169,6 +169,7 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
 
 template <typename T, bool kTrans>
 int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
+    ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
     // rows per CTA: at least 64, and no more CTAs than SMs (cooperative launch needs co-residency)
     int G = (m + 63) / 64;
     if (G > c->num_sms) G = c->num_sms;

@@ -88,7 +88,7 @@ __device__ __forceinline__ void window_op(T* __restrict__ A, size_t n, int kind,
 }
 
 template <typename T>
-__global__ void stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
+__global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Win = reinterpret_cast<T*>(smem_raw);
     const int c = band, w = band + 1;
@@ -140,6 +140,7 @@ int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) {
     if (n < 2 || band < 1) return SVDB200_E_SHAPE;
     if (n > (size_t)INT_MAX / 4) return SVDB200_E_CAPACITY;
     const int cb = (int)band;
+    ProfScope ps(c, 4, 4.0 * (double)band * (double)n * (double)n * sizeof(T));
     size_t smem = (size_t)(3 * cb * cb + 2 * cb + 8) * sizeof(T);
     int want = 2 * cb * cb;
     int nt = ((want + 31) / 32) * 32;
