@@ -184,7 +184,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
+    # A dedicated non-default stream: svdb200_set_stream(NULL) means "the handle's own stream", so
+    # the legacy default stream (handle 0) cannot carry the work; events must be recorded on the
+    # stream the kernels are launched on.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     nmax = max(sizes)
     handles = {suf: capi.Handle(nmax, BAND, dt, device=local_rank) for suf, dt in DTYPES}
     for h in handles.values():

@@ -67,13 +67,15 @@ bidiag_qr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict_
         for (int i = tid; i < n - 1; i += P) e[i] = e_g[i];
         __syncthreads();
     }
-    unsigned long long max_iter = (500ull * (unsigned long long)n) ^ 2ull;   // svd_serial.h:164 ('^' is XOR)
+    const unsigned long long max_iter_ref = (500ull * (unsigned long long)n) ^ 2ull;   // svd_serial.h:164 ('^' is XOR)
+    // sweep budget: the reference's for float; 64x for double (tighter threshold => more sweeps)
+    const unsigned long long max_iter = sizeof(T) == 4 ? max_iter_ref : 64ull * max_iter_ref;
     if (tid == 0) {
         // Criteria<T>::init (svd_serial.h:146-166); sigma[] doubles as scratch for lambda.
         // float: the reference's constants (eps 1e-8, umin 1e-10).  double: the reference does not
         // compile for double; its float-calibrated constants would cap the accuracy near 1e-7*sigma_1,
-        // above the 1e-10 bar, so the double instantiation scales them (eps 1e-16, umin 1e-20).
-        T eps = sizeof(T) == 4 ? (T)1e-8 : (T)1e-16, umin = sizeof(T) == 4 ? (T)1e-10 : (T)1e-20, tol = (T)100 * eps;
+        // above the 1e-10 bar, so the double instantiation scales them (eps 1e-16, umin 1e-17).
+        T eps = sizeof(T) == 4 ? (T)1e-8 : (T)1e-16, umin = sizeof(T) == 4 ? (T)1e-10 : (T)1e-17, tol = (T)100 * eps;
         T lam = RN<T>::abs(d[n - 1]), lmin = lam;
         for (int j = n - 2; j >= 0; --j) {
             lam = RN<T>::abs(d[j]) * lam / (lam + RN<T>::abs(e[j]));
@@ -85,7 +87,7 @@ bidiag_qr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict_
             mmin = mu < mmin ? mu : mmin;
         }
         T lb = lmin < mmin ? lmin : mmin;
-        T a = tol * lb, b = (T)max_iter * umin;
+        T a = tol * lb, b = (T)max_iter_ref * umin;
         sh_thr = a < b ? b : a;
         sh_low = 0;
         sh_up = n - 2;
@@ -96,6 +98,7 @@ bidiag_qr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict_
     unsigned long long iter = 0;
     long long passes = 0;
     int status = 0;
+    int want = 32, prev_lo = -1, prev_up = -1;       // sweeps per pass adapt to the deflation rate
     while (true) {
         if (tid == 0) {
             // svd_serial.h:386-407
@@ -111,11 +114,14 @@ bidiag_qr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict_
         if (sh_done) break;
         if (iter >= max_iter) { status = 1; break; }
         const int lo = sh_low, nd = sh_up - sh_low + 2;   // window d[lo .. lo+nd-1], e[lo .. lo+nd-2]
-        int lanes = P;
+        // A pass that ended without deflation doubles the number of pipelined sweeps, a deflation
+        // halves it: no long runs of sweeps on an already converged window, and few passes when
+        // convergence is slow.
+        if (sh_low == prev_lo && sh_up == prev_up) want = want * 2 > P ? P : want * 2;
+        else want = want / 2 < 32 ? 32 : want / 2;
+        prev_lo = sh_low; prev_up = sh_up;
+        int lanes = want < P ? want : P;
         if ((unsigned long long)lanes > max_iter - iter) lanes = (int)(max_iter - iter);
-        // few sweeps per pass while the window is short keeps the pipeline-fill overhead bounded
-        int cap = nd * 4 < 32 ? 32 : nd * 4;
-        if (lanes > cap) lanes = cap;
         T* dd = d + lo;
         T* ee = e + lo;
         Rot<T> rot = {(T)1, (T)0, (T)0}, rot_ = {(T)1, (T)0, (T)0};

@@ -41,6 +41,7 @@ struct Ctx {
     double ms_stage1 = 0, ms_stage2 = 0, ms_qr = 0, ms_h2d = 0, ms_d2h = 0;
     std::string last_error;
     int coop_supported = 0;
+    int cluster_ok = 16;           // largest thread-block-cluster size the panel kernel may use (0: none)
     // per-kernel-class profiling (svdb200_set_profile)
     int profile = 0;
     double prof_ms[SVDB200_PROFILE_CLASSES] = {};

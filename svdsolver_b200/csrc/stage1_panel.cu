@@ -3,51 +3,56 @@
 // svd_cuda_2.cu:1117) / csc586::gpu::brd_p1 (svd_cpu.h:370) and their helpers qr_cuda/lq_cuda
 // (svd_cuda_2.cu:881/959), hholder_cuda (797), wy_compact_cuda (838).
 //
-// Panel kernel (one cooperative launch per panel instead of ~25 launches per COLUMN):
+// Panel kernel (one launch per panel instead of ~25 launches per COLUMN):
 //   * the m x b panel is distributed by rows over G CTAs and stays resident in shared memory for
 //     the whole factorisation (an LQ row panel is loaded transposed, so one code path serves both);
-//   * per column ONE grid-wide all-reduce: every CTA publishes the dot products of the pivot
-//     column with all b columns over its rows (warp-shuffle reductions), the pivot-row owner
-//     publishes the pivot row; after the barrier every CTA forms ||x||, the Householder scalars
-//     (sign convention of svd_serial.h:194-201: H x = -sign(x0)||x|| e1), the rank-1 update
-//     coefficients and column j of the compact-WY factor S (= -T, svd_parallel.h:97-113)
-//     redundantly from the reduced vector -- no second synchronisation;
-//   * partial sums are combined in CTA order, so the result is deterministic.
+//   * per column ONE all-reduce: every CTA publishes the dot products of the pivot column with all
+//     b columns over its rows, the pivot-row owner publishes the pivot row; after the barrier every
+//     CTA forms ||x||, the Householder scalars (sign convention of svd_serial.h:194-201:
+//     H x = -sign(x0)||x|| e1), the rank-1 update coefficients and column j of the compact-WY
+//     factor S (= -T, svd_parallel.h:97-113) redundantly from the reduced vector;
+//   * two transports for the all-reduce:
+//       kCluster = true : the CTAs form ONE thread-block cluster (<= 16 CTAs); partial vectors live
+//                         in each CTA's shared memory and are read by the peers over DSMEM; the
+//                         barrier is barrier.cluster (~0.2 us).  Used whenever the panel fits the
+//                         cluster's shared memory (m*b*sizeof(T) <~ 3 MB).
+//       kCluster = false: cooperative grid over up to 148 CTAs, partials through L2, software grid
+//                         barrier (~2-3 us).  Used for the tall panels of large matrices.
+//   * partial sums are combined in a fixed association, so the result is deterministic.
 // Outputs: R (or L) written into A with exact zeros below the diagonal of the panel, V (m x b,
 // unit diagonal explicit), V2 = V S^T, and S.
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace svdb200 {
 namespace {
 
 constexpr int kPanelThreads = 256;
-
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+constexpr int kMaxCluster = 16;
 
 // Panel element (r, c): r in [0,m) along the reflector direction, c in [0,b).
 //   kTrans == false (QR): A[r*lda + c]        kTrans == true (LQ): A[c*lda + r]
-template <typename T, bool kTrans>
+template <typename T, bool kTrans, bool kCluster>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_cta, T* __restrict__ V, T* __restrict__ V2,
                     T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int G = gridDim.x, g = blockIdx.x;
     const int r0 = g * rows_per_cta;
     const int R = max(0, min(rows_per_cta, m - r0));     // local rows
     const int ld = b + 1;
-    T* Ps = reinterpret_cast<T*>(smem_raw);              // R x ld
+    const int slot = 2 * b;                              // b dots + b pivot-row values
+    T* lred = reinterpret_cast<T*>(smem_raw);            // 2 * slot : this CTA's published vectors (cluster mode)
+    T* Ps = lred + 2 * slot;                             // R x ld
     T* Ss = Ps + (size_t)rows_per_cta * ld;              // b x b
-    T* zs = Ss + b * b;                                  // b : local partial dots / reduced dots
+    T* zs = Ss + b * b;                                  // b : reduced dots
     T* piv = zs + b;                                     // b : pivot row
     T* fs = piv + b;                                     // b : update coefficients
     T* gs = fs + b;                                      // b : V_k^T v_j
-    T* taus = gs + b;                                    // b
+    T* psum = gs + b;                                    // blockDim : chunk sums
     unsigned gen = 0;
 
     // ---- load the local slice --------------------------------------------------------------------
@@ -66,27 +71,56 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
     __syncthreads();
 
     const int kmax = min(b, m);
-    const int slot = 2 * b;                               // per-CTA scratch: b dots + b pivot-row values
+    const int rgroups = max(1, nt / b);                  // thread (c = tid % b, grp = tid / b)
     for (int j = 0; j < kmax; ++j) {
-        T* buf = red + (size_t)(j & 1) * (G + 1) * slot;
         // ---- phase A: local dots of column j (rows > j) with every column ---------------------------
         const int lo = max(0, j + 1 - r0);               // first local row with global index > j
-        for (int c = warp; c < b; c += nwarps) {
+        if (tid < rgroups * b) {
+            const int c = tid % b, grp = tid / b;
             T acc = (T)0;
-            for (int rl = lo + lane; rl < R; rl += 32) acc += Ps[rl * ld + c] * Ps[rl * ld + j];
-            acc = warp_sum(acc);
-            if (lane == 0) st_cg(&buf[(size_t)g * slot + c], acc);
+            for (int rl = lo + grp; rl < R; rl += rgroups) acc += Ps[rl * ld + c] * Ps[rl * ld + j];
+            psum[grp * b + c] = acc;
         }
-        if (j >= r0 && j < r0 + R) {                     // owner of the pivot row publishes it
-            for (int c = tid; c < b; c += nt) st_cg(&buf[(size_t)G * slot + c], Ps[(j - r0) * ld + c]);
-        }
-        grid_barrier(bar, (unsigned)G, gen);
-        // ---- phase B: ordered reduction (deterministic) ----------------------------------------------
+        __syncthreads();
+        T* mine = kCluster ? lred + (j & 1) * slot : red + ((size_t)(j & 1) * (G + 1) + g) * slot;
+        T* pivslot = kCluster ? lred + (j & 1) * slot + b : red + ((size_t)(j & 1) * (G + 1) + G) * slot;
+        const bool owner = (j >= r0 && j < r0 + R);
         for (int c = tid; c < b; c += nt) {
-            T acc = (T)0;
-            for (int q = 0; q < G; ++q) acc += ld_cg(&buf[(size_t)q * slot + c]);
-            zs[c] = acc;
-            piv[c] = ld_cg(&buf[(size_t)G * slot + c]);
+            T acc = psum[c];
+            for (int grp = 1; grp < rgroups; ++grp) acc += psum[grp * b + c];
+            if (kCluster) mine[c] = acc; else st_cg(&mine[c], acc);
+            if (owner) {
+                if (kCluster) pivslot[c] = Ps[(j - r0) * ld + c]; else st_cg(&pivslot[c], Ps[(j - r0) * ld + c]);
+            }
+        }
+        if (kCluster) cg::this_cluster().sync(); else grid_barrier(bar, (unsigned)G, gen);
+        // ---- phase B: all-reduce in a fixed association ------------------------------------------------
+        {
+            const int chunk = (G + rgroups - 1) / rgroups;
+            const int jowner = j / rows_per_cta;
+            if (tid < rgroups * b) {
+                const int c = tid % b, part = tid / b;
+                const int q0 = part * chunk, q1 = min(G, q0 + chunk);
+                T acc = (T)0;
+                if (kCluster) {
+                    cg::cluster_group cl = cg::this_cluster();
+#pragma unroll 4
+                    for (int q = q0; q < q1; ++q) acc += cl.map_shared_rank(lred, q)[(j & 1) * slot + c];
+                    if (part == 0) piv[c] = cl.map_shared_rank(lred, jowner)[(j & 1) * slot + b + c];
+                } else {
+                    const T* buf = red + (size_t)(j & 1) * (G + 1) * slot;
+#pragma unroll 8
+                    for (int q = q0; q < q1; ++q) acc += ld_cg(&buf[(size_t)q * slot + c]);
+                    if (part == 0) piv[c] = ld_cg(&buf[(size_t)G * slot + c]);
+                }
+                psum[part * b + c] = acc;
+            }
+            __syncthreads();
+            for (int c = tid; c < b; c += nt) {
+                T acc = psum[c];
+                for (int part = 1; part < rgroups; ++part) acc += psum[part * b + c];
+                zs[c] = acc;
+            }
         }
         __syncthreads();
         // ---- phase C: scalars, S column, rank-1 update --------------------------------------------------
@@ -107,7 +141,9 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
                 gs[c] = piv[c] + alpha * zs[c];
             }
         }
-        if (tid == 0) taus[j] = tau;
+        // scale the pivot column into w (rows > j), store beta on the pivot row
+        for (int rl = lo + tid; rl < R; rl += nt) Ps[rl * ld + j] *= alpha;
+        if (owner && tid == 0) Ps[(j - r0) * ld + j] = beta;
         __syncthreads();
         // S[0:j, j] = -tau * S[0:j,0:j] * g ; S[j][j] = -tau   (svd_parallel.h:102-111)
         if (tid < j) {
@@ -117,10 +153,6 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
         } else if (tid == j) {
             Ss[j * b + j] = -tau;
         }
-        // scale the pivot column into w (rows > j), store beta on the pivot row
-        for (int rl = lo + tid; rl < R; rl += nt) Ps[rl * ld + j] *= alpha;
-        if (j >= r0 && j < r0 + R && tid == 0) Ps[(j - r0) * ld + j] = beta;
-        __syncthreads();
         // rows >= j, columns > j :  a_rc -= w_r * f_c
         const int lo2 = max(0, j - r0);
         const int ncu = b - j - 1;
@@ -165,28 +197,68 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
         }
     }
     if (g == 0) for (int e = tid; e < b * b; e += nt) S_out[e] = Ss[e];
+    // no CTA may exit while a peer can still read its shared memory
+    if (kCluster) cg::this_cluster().sync();
+}
+
+inline size_t panel_smem_bytes(int rows, int b, size_t esz) {
+    return ((size_t)4 * b + (size_t)rows * (b + 1) + (size_t)b * b + 4 * (size_t)b + kPanelThreads + 8) * esz;
 }
 
 template <typename T, bool kTrans>
 int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
-    // rows per CTA: at least 64, and no more CTAs than SMs (cooperative launch needs co-residency)
+    T* V = reinterpret_cast<T*>(c->v);
+    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* S = reinterpret_cast<T*>(c->s);
+    T* red = reinterpret_cast<T*>(c->red);
+    unsigned* bar = c->bar;
+    // ---- cluster transport when the panel fits the shared memory of one cluster ---------------------
+    if (c->cluster_ok) {
+        int G = (m + 31) / 32;
+        if (G > c->cluster_ok) G = c->cluster_ok;
+        if (G < 1) G = 1;
+        int rows = (m + G - 1) / G;
+        G = (m + rows - 1) / rows;
+        size_t smem = panel_smem_bytes(rows, b, sizeof(T));
+        if (smem <= 200 * 1024) {
+            auto kern = panel_factor_kernel<T, kTrans, true>;
+            SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (G > 8) SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(kPanelThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = c->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = G;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, rows, V, V2, S, red, bar);
+            if (e == cudaSuccess) {
+                c->launches++;
+                return 0;
+            }
+            cudaGetLastError();           // cluster shape not schedulable here: use the grid transport
+            c->cluster_ok = c->cluster_ok > 8 ? 8 : 0;
+            return launch_panel<T, kTrans>(c, a, lda, m, b);
+        }
+    }
+    // ---- cooperative-grid transport -----------------------------------------------------------------------
     int G = (m + 63) / 64;
     if (G > c->num_sms) G = c->num_sms;
     if (G > kMaxPanelCtas) G = kMaxPanelCtas;
     if (G < 1) G = 1;
     int rows = (m + G - 1) / G;
     G = (m + rows - 1) / rows;
-    size_t smem = ((size_t)rows * (b + 1) + (size_t)b * b + 5 * (size_t)b + 8) * sizeof(T);
+    size_t smem = panel_smem_bytes(rows, b, sizeof(T));
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
-    auto kern = panel_factor_kernel<T, kTrans>;
+    auto kern = panel_factor_kernel<T, kTrans, false>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), c->stream));
-    T* V = reinterpret_cast<T*>(c->v);
-    T* V2 = reinterpret_cast<T*>(c->v2);
-    T* S = reinterpret_cast<T*>(c->s);
-    T* red = reinterpret_cast<T*>(c->red);
-    unsigned* bar = c->bar;
     void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar};
     SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, c->stream));
     c->launches++;

@@ -2,14 +2,19 @@
 // (svd_parallel.h:640-695; kernels band_rd_top 569-589, band_rd_right 600-608, band_rd_left 617-624).
 //
 // B200 design
-//   * one CTA per in-flight sweep; sweeps are pipelined across SMs: pair p of sweep i+1 may start
-//     once sweep i has completed pair p+2 (window-overlap analysis, DESIGN.md / SURVEY 8a''),
-//     enforced with one per-sweep progress counter in global memory (st.release / ld.acquire);
-//   * the band region (n*(3b) elements) is L2-resident; windows are staged in shared memory and all
-//     inter-CTA data goes through L2 (ld.global.cg), never the non-coherent L1;
+//   * one CTA per in-flight sweep; sweeps are pipelined across SMs.  Window op q of sweep i+1
+//     (ops numbered RIGHT(p) = 2p, LEFT(p) = 2p+1) overlaps ops of sweep i only up to index q+3
+//     (brute-force check in tests/test_oracle.py), so it may start once sweep i has completed
+//     q+4 ops: one per-sweep progress counter in global memory (st.release / ld.acquire);
+//   * consecutive ops of a sweep share half of their window: RIGHT(p) = [F; N] hands its lower
+//     block to LEFT(p) = [F | N], which hands its right block to RIGHT(p+1).  The forwarded block F
+//     never leaves shared memory; only the new block N (c x c) is fetched from L2 -- and that fetch
+//     is overlapped with the norm / Householder / H computation, which needs F only -- and only the
+//     finished block is written back.  All inter-CTA data goes through L2 (ld.global.cg /
+//     st.global.cg), never the non-coherent L1;
 //   * arithmetic is BIT-FAITHFUL to the reference: explicit H = I - tau w w^T, window*H / H*window
 //     with k-ascending sums from 0, separate (never fused) multiply and add, reflector scalars in
-//     double -- so the kernel reproduces data/bidiagonal_* exactly when fed data/band_* (SURVEY 0.7).
+//     double -- so the kernel reproduces data/bidiagonal_* exactly when fed data/band_* (SURVEY 0.7);
 //   * the reference's window schedule is reproduced including its boundary behaviour.
 #include <climits>
 #include "common.cuh"
@@ -18,109 +23,194 @@ namespace svdb200 {
 
 namespace {
 
-constexpr int kEptMax = 8;   // outputs per thread (2*c*c / blockDim) upper bound
+// Thread tiling of one window product C = X * Y (nr x L times L x nc): every thread owns a 4 x 2
+// register tile (rows ry + q*RT, columns cx and cx + CT).  Lanes of a warp run along the columns,
+// so Y loads are conflict-free and X loads are broadcasts; odd leading dimensions keep the (at
+// most two) distinct X rows of a warp in different banks.
+constexpr int kTileR = 4, kTileC = 2, kNewPerThread = 4;
 
-// One window operation. kind 0: A_t <- A_t * H(first row); kind 1: A_t <- H(first column) * A_t.
+__host__ __device__ inline int stage2_threads(int c) {
+    int ct = (c + 1) / 2;
+    int need = ct * ct;                         // RIGHT: CT = RT = ceil(c/2); LEFT: CT = c, RT = ceil(c/4)
+    int need_left = c * ((c + 3) / 4);
+    if (need_left > need) need = need_left;
+    return ((need + 31) / 32) * 32;
+}
+
+// Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.
 template <typename T>
-__device__ __forceinline__ void window_op(T* __restrict__ A, size_t n, int kind, int i1, int i2, int j1, int j2,
-                                          T* Win, T* H, T* wv, T* sc) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int nr = i2 - i1, nc = j2 - j1;
-    const int tot = nr * nc;
-    for (int e = tid; e < tot; e += nt) {
-        int r = e / nc, cc = e - r * nc;
-        Win[e] = ld_cg(&A[(size_t)(i1 + r) * n + (j1 + cc)]);
+__device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* sc) {
+    T acc = (T)0;
+    int i = 0;
+    for (; i + 8 <= L; i += 8) {               // the loads are independent: let them pipeline
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = x[(i + u) * xs];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = RN<T>::add(acc, RN<T>::mul(v[u], v[u]));
     }
-    __syncthreads();
-    const int L = kind == 0 ? nc : nr;        // reflector length
-    const int xs = kind == 0 ? 1 : nc;        // stride of x inside Win
-    if (tid == 0) {
-        T acc = (T)0;
-        for (int i = 0; i < L; ++i) {          // matrix.h:59-62: index-order, unfused
-            T x = Win[i * xs];
-            acc = RN<T>::add(acc, RN<T>::mul(x, x));
-        }
-        T alpha, tau;
-        householder_scalars<T>(Win[0], RN<T>::sqrt(acc), alpha, tau);
-        sc[0] = alpha;
-        sc[1] = tau;
+    for (; i < L; ++i) {
+        T v = x[i * xs];
+        acc = RN<T>::add(acc, RN<T>::mul(v, v));
     }
-    __syncthreads();
-    const T alpha = sc[0];
-    const T mtau = -sc[1];
-    for (int i = tid; i < L; i += nt) wv[i] = (i == 0) ? (T)1 : RN<T>::mul(Win[i * xs], alpha);
-    __syncthreads();
-    for (int e = tid; e < L * L; e += nt) {    // svd_serial.h:204-211
+    T alpha, tau;
+    householder_scalars<T>(x[0], RN<T>::sqrt(acc), alpha, tau);
+    sc[0] = alpha;
+    sc[1] = tau;
+}
+
+// H = I - tau w w^T exactly as svd_serial.h:199-211 (w_0 = 1, w_i = x_i * alpha).
+template <typename T>
+__device__ __forceinline__ void build_h(const T* x, int xs, int L, const T* sc, T* H, int ldh) {
+    const T alpha = sc[0], mtau = -sc[1];
+    for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
         int i = e / L, j = e - i * L;
-        T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wv[i], wv[j])), mtau);
+        T wi = (i == 0) ? (T)1 : RN<T>::mul(x[i * xs], alpha);
+        T wj = (j == 0) ? (T)1 : RN<T>::mul(x[j * xs], alpha);
+        T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wi, wj)), mtau);
         if (i == j) h = RN<T>::add((T)1, h);
-        H[e] = h;
+        H[i * ldh + j] = h;
     }
-    __syncthreads();
-    T acc[kEptMax];
-    int rr[kEptMax], cc_[kEptMax];
+}
+
+// out(nr x nc) = X(nr x L) * Y(L x nc), k ascending from +0, unfused (matrix.h:243-246).
+// Every finished element is handed to sink(r, cc, value).
+template <typename T, typename Sink>
+__device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, int ldy, int nr, int nc, int L, int CT, int RT,
+                                               Sink sink) {
+    const int tid = threadIdx.x;
+    const int cx = tid % CT, ry = tid / CT;
+    if (ry >= RT) return;
+    T acc[kTileR][kTileC];
 #pragma unroll
-    for (int q = 0; q < kEptMax; ++q) {
-        int e = tid + q * nt;
-        acc[q] = (T)0;
-        rr[q] = (e < tot) ? e / nc : 0;
-        cc_[q] = (e < tot) ? e - rr[q] * nc : 0;
-    }
-    if (kind == 0) {
-        for (int k = 0; k < L; ++k) {
+    for (int q = 0; q < kTileR; ++q)
 #pragma unroll
-            for (int q = 0; q < kEptMax; ++q)
-                acc[q] = RN<T>::add(acc[q], RN<T>::mul(Win[rr[q] * nc + k], H[k * L + cc_[q]]));
+        for (int s2 = 0; s2 < kTileC; ++s2) acc[q][s2] = (T)0;
+    int xr[kTileR];
+#pragma unroll
+    for (int q = 0; q < kTileR; ++q) xr[q] = min(ry + q * RT, nr - 1) * ldx;
+    const int y0 = min(cx, nc - 1), y1 = min(cx + CT, nc - 1);
+    for (int k = 0; k < L; ++k) {
+        const T yv0 = Y[k * ldy + y0], yv1 = Y[k * ldy + y1];
+#pragma unroll
+        for (int q = 0; q < kTileR; ++q) {
+            const T xv = X[xr[q] + k];
+            acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv, yv0));
+            acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv, yv1));
         }
-    } else {
-        for (int k = 0; k < L; ++k) {
+    }
 #pragma unroll
-            for (int q = 0; q < kEptMax; ++q)
-                acc[q] = RN<T>::add(acc[q], RN<T>::mul(H[rr[q] * L + k], Win[k * nc + cc_[q]]));
+    for (int q = 0; q < kTileR; ++q) {
+        const int r = ry + q * RT;
+        if (r < nr) {
+            if (cx < nc) sink(r, cx, acc[q][0]);
+            if (cx + CT < nc) sink(r, cx + CT, acc[q][1]);
         }
     }
-#pragma unroll
-    for (int q = 0; q < kEptMax; ++q) {
-        int e = tid + q * nt;
-        if (e < tot) st_cg(&A[(size_t)(i1 + rr[q]) * n + (j1 + cc_[q])], acc[q]);
-    }
-    __syncthreads();
 }
 
 template <typename T>
 __global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* Win = reinterpret_cast<T*>(smem_raw);
     const int c = band, w = band + 1;
-    T* H = Win + 2 * c * c + c;
-    T* wv = H + c * c;
-    T* sc = wv + c;
-    const int tid = threadIdx.x;
+    const int ldr = c + 1, ldl = 2 * c + 1, ldh = c + 1;
+    T* WR = reinterpret_cast<T*>(smem_raw);     // RIGHT window [2c][c+1]
+    T* WL = WR + 2 * c * ldr;                   // LEFT  window [c][2c+1]
+    T* H = WL + c * ldl;                        // [c][c+1]
+    T* sc = H + c * ldh;                        // alpha, tau
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t N = (size_t)n;
+
     for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
         const int top_j2 = min(i + 2 * w - 1, n);
         const int npairs = 1 + (n - top_j2) / c + 1;
+        int fr = 0;                               // rows of the forwarded block sitting in WR (0: none)
         for (int p = 0; p < npairs; ++p) {
-            if (i > 0) {
-                if (tid == 0) {
-                    while (ld_acquire(&prog[i - 1]) < p + 3) __nanosleep(40);
+            const int r0 = (p == 0) ? i : min(i + 1 + (p - 1) * c, n);
+            const int r1 = min(i + 1 + p * c, n), r2 = min(i + 1 + (p + 1) * c, n), c3 = min(i + 1 + (p + 2) * c, n);
+            if (r2 <= r1) break;                  // empty pair (only possible as the very last one)
+            // ================= RIGHT(p): rows [r0,r2) x cols [r1,r2), window = [F; N] ===================
+            {
+                const int q = 2 * p;
+                if (i > 0) {
+                    if (tid == 0) while (ld_acquire(&prog[i - 1]) < q + 4) __nanosleep(20);
+                    __syncthreads();
+                }
+                const int nc = r2 - r1, nr = r2 - r0;
+                const int have = fr;              // rows [0,have) of WR already hold F
+                T nv[kNewPerThread];
+                const int newcnt = (nr - have) * nc;
+                if (have == 0) {                  // top pair: the whole window (x included) comes from L2
+                    for (int e = tid; e < newcnt; e += nt)
+                        WR[(e / nc) * ldr + e % nc] = ld_cg(&A[(size_t)(r0 + e / nc) * N + (r1 + e % nc)]);
+                    __syncthreads();
+                } else {                          // issue the fetch of N, consume it after H is built
+#pragma unroll
+                    for (int u = 0; u < kNewPerThread; ++u) {
+                        int e = tid + u * nt;
+                        if (e < newcnt) nv[u] = ld_cg(&A[(size_t)(r0 + have + e / nc) * N + (r1 + e % nc)]);
+                    }
+                }
+                if (tid == 0) reflector_scalars<T>(WR, 1, nc, sc);
+                __syncthreads();
+                build_h<T>(WR, 1, nc, sc, H, ldh);
+                if (have != 0) {
+#pragma unroll
+                    for (int u = 0; u < kNewPerThread; ++u) {
+                        int e = tid + u * nt;
+                        if (e < newcnt) WR[(have + e / nc) * ldr + e % nc] = nv[u];
+                    }
                 }
                 __syncthreads();
+                // rows [r0,r1) are finished for this sweep; rows [r1,r2) become LEFT(p)'s left block
+                const int keep = r1 - r0;
+                window_product<T>(WR, ldr, H, ldh, nr, nc, nc, (c + 1) / 2, (c + 1) / 2,
+                                  [&](int r, int cc, T v) {
+                                      if (r < keep) st_cg(&A[(size_t)(r0 + r) * N + (r1 + cc)], v);
+                                      else WL[(r - keep) * ldl + cc] = v;
+                                  });
+                __syncthreads();
+                if (tid == 0) st_release(&prog[i], q + 1);
             }
-            if (p == 0) {
-                window_op<T>(A, (size_t)n, 0, i, min(i + w, n), i + 1, min(i + w, n), Win, H, wv, sc);
-                window_op<T>(A, (size_t)n, 1, i + 1, min(i + w, n), i + 1, top_j2, Win, H, wv, sc);
-            } else {
-                const int k = p - 1;
-                const int r0 = min(i + 1 + k * c, n), r1 = min(i + 1 + (k + 1) * c, n);
-                const int r2 = min(i + 1 + (k + 2) * c, n), c3 = min(i + 1 + (k + 3) * c, n);
-                if (r2 > r1) window_op<T>(A, (size_t)n, 0, r0, r2, r1, r2, Win, H, wv, sc);
-                if (c3 > r1) window_op<T>(A, (size_t)n, 1, r1, r2, r1, c3, Win, H, wv, sc);
+            // ================= LEFT(p): rows [r1,r2) x cols [r1,c3), window = [F | N] ====================
+            const int nn = c3 - r2;
+            const bool fwd = (p + 1 < npairs) && nn > 0;   // is there a RIGHT(p+1) to hand the right block to
+            {
+                const int q = 2 * p + 1;
+                if (i > 0) {
+                    if (tid == 0) while (ld_acquire(&prog[i - 1]) < q + 4) __nanosleep(20);
+                    __syncthreads();
+                }
+                const int nr = r2 - r1, fc = r2 - r1, nc = fc + nn;
+                T nv[kNewPerThread];
+                const int newcnt = nr * nn;
+#pragma unroll
+                for (int u = 0; u < kNewPerThread; ++u) {
+                    int e = tid + u * nt;
+                    if (e < newcnt) nv[u] = ld_cg(&A[(size_t)(r1 + e / nn) * N + (r2 + e % nn)]);
+                }
+                if (tid == 0) reflector_scalars<T>(WL, ldl, nr, sc);
+                __syncthreads();
+                build_h<T>(WL, ldl, nr, sc, H, ldh);
+#pragma unroll
+                for (int u = 0; u < kNewPerThread; ++u) {
+                    int e = tid + u * nt;
+                    if (e < newcnt) WL[(e / nn) * ldl + fc + e % nn] = nv[u];
+                }
+                __syncthreads();
+                // cols [r1,r2) are finished; cols [r2,c3) become the top block of RIGHT(p+1)
+                window_product<T>(H, ldh, WL, ldl, nr, nc, nr, c, (c + 3) / 4,
+                                  [&](int r, int cc, T v) {
+                                      if (cc < fc || !fwd) st_cg(&A[(size_t)(r1 + r) * N + (r1 + cc)], v);
+                                      else WR[r * ldr + (cc - fc)] = v;
+                                  });
+                fr = fwd ? nr : 0;
+                __syncthreads();
+                if (tid == 0 && fwd) st_release(&prog[i], q + 1);
             }
-            if (tid == 0) {
-                __threadfence();
-                st_release(&prog[i], p + 1 == npairs ? INT_MAX : p + 1);
-            }
+            if (!fwd) break;
         }
+        if (tid == 0) st_release(&prog[i], INT_MAX);
     }
 }
 
@@ -141,20 +231,18 @@ int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) {
     if (n > (size_t)INT_MAX / 4) return SVDB200_E_CAPACITY;
     const int cb = (int)band;
     ProfScope ps(c, 4, 4.0 * (double)band * (double)n * (double)n * sizeof(T));
-    size_t smem = (size_t)(3 * cb * cb + 2 * cb + 8) * sizeof(T);
-    int want = 2 * cb * cb;
-    int nt = ((want + 31) / 32) * 32;
-    if (nt < 32) nt = 32;
-    if (nt > 1024) nt = 1024;
-    if ((2 * cb * cb + nt - 1) / nt > kEptMax) return SVDB200_E_CAPACITY;
+    size_t smem = (size_t)(2 * cb * (cb + 1) + cb * (2 * cb + 1) + cb * (cb + 1) + 8) * sizeof(T);
+    int nt = stage2_threads(cb);
+    if (nt > 1024) return SVDB200_E_CAPACITY;      // band <= 64
+    if (cb * cb > kNewPerThread * nt) return SVDB200_E_CAPACITY;
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
     auto kern = stage2_chase_kernel<T>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVDB_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) return SVDB200_E_CAPACITY;
-    // No more sweeps can be in flight than the pipeline admits (one every 3 pairs, SURVEY 8a'').
-    long long inflight = (long long)(n / band) / 3 + 2;
+    // No more sweeps can be in flight than the pipeline admits (one every 2 pairs).
+    long long inflight = (long long)(n / band) / 2 + 2;
     long long grid = (long long)per_sm * c->num_sms;
     if (grid > inflight) grid = inflight;
     if (grid > (long long)n - 1) grid = (long long)n - 1;

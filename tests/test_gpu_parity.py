@@ -169,20 +169,25 @@ def test_trailing_update_gemms(capi, suf, m, n, b):
     Ut = torch.rand(n, b, device="cuda", dtype=dt, generator=g) - 0.5
     Q = torch.rand(b, n, device="cuda", dtype=dt, generator=g) - 0.5
     tol = 2e-5 if suf == "f32" else 1e-12
+    torch.cuda.synchronize()
     with handle(capi, max(m, n) + 64, b, suf) as h:
-        h.set_stream(torch.cuda.current_stream().cuda_stream)
         W = torch.empty(b, n, device="cuda", dtype=dt)
+        torch.cuda.synchronize()
         h.gemm_tn_dev(V.data_ptr(), C.data_ptr(), ld, m, n, b, W.data_ptr())
+        h.synchronize()
         ref = (V.double().T @ C[:, :n].double())
         assert (W.double() - ref).abs().max().item() <= tol * ref.abs().max().item()
         W2 = torch.empty(m, b, device="cuda", dtype=dt)
+        torch.cuda.synchronize()
         h.gemm_nn_dev(C.data_ptr(), ld, m, n, b, Ut.data_ptr(), W2.data_ptr())
+        h.synchronize()
         ref2 = C[:, :n].double() @ Ut.double()
         assert (W2.double() - ref2).abs().max().item() <= tol * ref2.abs().max().item()
         C2 = C.clone()
-        h.rank_update_dev(C2.data_ptr(), ld, m, n, b, V.data_ptr(), Q.data_ptr(), n)
-        ref3 = C[:, :n].double() + V.double() @ Q.double()
         torch.cuda.synchronize()
+        h.rank_update_dev(C2.data_ptr(), ld, m, n, b, V.data_ptr(), Q.data_ptr(), n)
+        h.synchronize()
+        ref3 = C[:, :n].double() + V.double() @ Q.double()
         assert (C2[:, :n].double() - ref3).abs().max().item() <= tol * ref3.abs().max().item()
         assert torch.equal(C2[:, n:], C[:, n:])          # padding columns untouched
 
