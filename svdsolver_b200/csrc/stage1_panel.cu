@@ -30,7 +30,6 @@ namespace svdb200 {
 namespace {
 
 constexpr int kPanelThreads = 256;
-constexpr int kMaxCluster = 16;
 
 // Panel element (r, c): r in [0,m) along the reflector direction, c in [0,b).
 //   kTrans == false (QR): A[r*lda + c]        kTrans == true (LQ): A[c*lda + r]
@@ -47,39 +46,37 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
     const int slot = 2 * b;                              // b dots + b pivot-row values
     T* lred = reinterpret_cast<T*>(smem_raw);            // 2 * slot : this CTA's published vectors (cluster mode)
     T* Ps = lred + 2 * slot;                             // R x ld
-    T* Ss = Ps + (size_t)rows_per_cta * ld;              // b x b
-    T* zs = Ss + b * b;                                  // b : reduced dots
+    T* Gm = Ps + (size_t)rows_per_cta * ld;              // b x b : Gm[c][j] = v_c^T v_j (c < j)
+    T* zs = Gm + b * b;                                  // b : reduced dots
     T* piv = zs + b;                                     // b : pivot row
     T* fs = piv + b;                                     // b : update coefficients
-    T* gs = fs + b;                                      // b : V_k^T v_j
-    T* psum = gs + b;                                    // blockDim : chunk sums
+    T* taus = fs + b;                                    // b
+    T* psum = taus + b;                                  // blockDim : chunk sums
     unsigned gen = 0;
+    const int tx = tid % b, tyy = tid / b;               // 2-D view: b columns x rgroups rows
+    const int rgroups = max(1, nt / b);
+    const bool in2d = tyy < rgroups;
+    const int lane = tid & 31, wrp = tid >> 5, nwarps = nt >> 5;
 
     // ---- load the local slice --------------------------------------------------------------------
     if (!kTrans) {
-        for (int e = tid; e < R * b; e += nt) {
-            int rl = e / b, c = e - rl * b;
-            Ps[rl * ld + c] = A[(size_t)(r0 + rl) * lda + c];
-        }
+        if (in2d)
+            for (int rl = tyy; rl < R; rl += rgroups) Ps[rl * ld + tx] = A[(size_t)(r0 + rl) * lda + tx];
     } else {
-        for (int e = tid; e < R * b; e += nt) {
-            int c = e / R, rl = e - c * R;
-            Ps[rl * ld + c] = A[(size_t)c * lda + (r0 + rl)];
-        }
+        for (int c = wrp; c < b; c += nwarps)
+            for (int rl = lane; rl < R; rl += 32) Ps[rl * ld + c] = A[(size_t)c * lda + (r0 + rl)];
     }
-    for (int e = tid; e < b * b; e += nt) Ss[e] = (T)0;
+    for (int e = tid; e < b * b; e += nt) Gm[e] = (T)0;
     __syncthreads();
 
     const int kmax = min(b, m);
-    const int rgroups = max(1, nt / b);                  // thread (c = tid % b, grp = tid / b)
     for (int j = 0; j < kmax; ++j) {
         // ---- phase A: local dots of column j (rows > j) with every column ---------------------------
         const int lo = max(0, j + 1 - r0);               // first local row with global index > j
-        if (tid < rgroups * b) {
-            const int c = tid % b, grp = tid / b;
+        if (in2d) {
             T acc = (T)0;
-            for (int rl = lo + grp; rl < R; rl += rgroups) acc += Ps[rl * ld + c] * Ps[rl * ld + j];
-            psum[grp * b + c] = acc;
+            for (int rl = lo + tyy; rl < R; rl += rgroups) acc += Ps[rl * ld + tx] * Ps[rl * ld + j];
+            psum[tyy * b + tx] = acc;
         }
         __syncthreads();
         T* mine = kCluster ? lred + (j & 1) * slot : red + ((size_t)(j & 1) * (G + 1) + g) * slot;
@@ -98,8 +95,8 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
         {
             const int chunk = (G + rgroups - 1) / rgroups;
             const int jowner = j / rows_per_cta;
-            if (tid < rgroups * b) {
-                const int c = tid % b, part = tid / b;
+            if (in2d) {
+                const int c = tx, part = tyy;
                 const int q0 = part * chunk, q1 = min(G, q0 + chunk);
                 T acc = (T)0;
                 if (kCluster) {
@@ -123,7 +120,7 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
             }
         }
         __syncthreads();
-        // ---- phase C: scalars, S column, rank-1 update --------------------------------------------------
+        // ---- phase C: scalars, Gram column, rank-1 update -----------------------------------------------
         const T x0 = piv[j];
         const T normsq = zs[j] + x0 * x0;
         const T nrm = sqrt(normsq);
@@ -137,66 +134,95 @@ panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_ct
                 // w^T a_c with w = [1; alpha*x_{>j}] :  piv[c] + alpha * sum_{r>j} x_r a_rc
                 fs[c] = tau * (piv[c] + alpha * zs[c]);
             } else if (c < j) {
-                // V[:,c]^T v_j = V[j][c] * 1 + alpha * sum_{r>j} V[r][c] x_r
-                gs[c] = piv[c] + alpha * zs[c];
+                // v_c^T v_j = V[j][c] * 1 + alpha * sum_{r>j} V[r][c] x_r
+                Gm[c * b + j] = piv[c] + alpha * zs[c];
+            } else {
+                taus[j] = tau;
             }
         }
         // scale the pivot column into w (rows > j), store beta on the pivot row
         for (int rl = lo + tid; rl < R; rl += nt) Ps[rl * ld + j] *= alpha;
         if (owner && tid == 0) Ps[(j - r0) * ld + j] = beta;
         __syncthreads();
-        // S[0:j, j] = -tau * S[0:j,0:j] * g ; S[j][j] = -tau   (svd_parallel.h:102-111)
-        if (tid < j) {
-            T acc = (T)0;
-            for (int c = tid; c < j; ++c) acc += Ss[tid * b + c] * gs[c];   // S upper triangular
-            Ss[tid * b + j] = -tau * acc;
-        } else if (tid == j) {
-            Ss[j * b + j] = -tau;
-        }
         // rows >= j, columns > j :  a_rc -= w_r * f_c
-        const int lo2 = max(0, j - r0);
-        const int ncu = b - j - 1;
-        if (ncu > 0) {
-            for (int e = tid; e < (R - lo2) * ncu; e += nt) {
-                int rl = lo2 + e / ncu, c = j + 1 + e % ncu;
+        if (in2d && tx > j) {
+            const int lo2 = max(0, j - r0);
+            const T f = fs[tx];
+            for (int rl = lo2 + tyy; rl < R; rl += rgroups) {
                 T wv = (r0 + rl == j) ? (T)1 : Ps[rl * ld + j];
-                Ps[rl * ld + c] -= wv * fs[c];
+                Ps[rl * ld + tx] -= wv * f;
             }
         }
         __syncthreads();
     }
 
-    // ---- epilogue: V, V2 = V S^T, S, and the factored panel back into A ---------------------------
-    // V(row, k) = 1 (row == k), Ps (row > k), 0 (row < k)
-    for (int e = tid; e < R * b; e += nt) {
-        int rl = e / b, c = e - rl * b;
-        int row = r0 + rl;
-        T vv = (row == c) ? (T)1 : (row > c ? Ps[rl * ld + c] : (T)0);
-        if (c >= kmax) vv = (T)0;
-        T acc = (T)0;                                     // V2[row][c] = sum_{k >= c} V[row][k] * S[c][k]
-        int khi = min(kmax - 1, row);
-        for (int k = c; k <= khi; ++k) {
-            T vk = (row == k) ? (T)1 : Ps[rl * ld + k];
-            acc += vk * Ss[c * b + k];
-        }
-        V[(size_t)row * b + c] = vv;
-        if (!kTrans) V2[(size_t)row * b + c] = acc;
-        else V2[(size_t)c * m + row] = acc;
-    }
+    // ---- epilogue ------------------------------------------------------------------------------------
+    // V(row, k) = 1 (row == k), Ps (row > k), 0 (row < k); the factored panel goes back into A with
+    // exact zeros below the diagonal.
     if (!kTrans) {
-        for (int e = tid; e < R * b; e += nt) {
-            int rl = e / b, c = e - rl * b;
-            int row = r0 + rl;
-            A[(size_t)row * lda + c] = (c >= row) ? Ps[rl * ld + c] : (T)0;
-        }
+        if (in2d)
+            for (int rl = tyy; rl < R; rl += rgroups) {
+                const int row = r0 + rl, c = tx;
+                T vv = (row == c) ? (T)1 : (row > c ? Ps[rl * ld + c] : (T)0);
+                if (c >= kmax) vv = (T)0;
+                V[(size_t)row * b + c] = vv;
+                A[(size_t)row * lda + c] = (c >= row) ? Ps[rl * ld + c] : (T)0;
+            }
     } else {
-        for (int e = tid; e < R * b; e += nt) {
-            int c = e / R, rl = e - c * R;
-            int row = r0 + rl;
-            A[(size_t)c * lda + row] = (c >= row) ? Ps[rl * ld + c] : (T)0;
+        if (in2d)
+            for (int rl = tyy; rl < R; rl += rgroups) {
+                const int row = r0 + rl, c = tx;
+                T vv = (row == c) ? (T)1 : (row > c ? Ps[rl * ld + c] : (T)0);
+                if (c >= kmax) vv = (T)0;
+                V[(size_t)row * b + c] = vv;
+            }
+        for (int c = wrp; c < b; c += nwarps)
+            for (int rl = lane; rl < R; rl += 32) {
+                const int row = r0 + rl;
+                A[(size_t)c * lda + row] = (c >= row) ? Ps[rl * ld + c] : (T)0;
+            }
+    }
+    __syncthreads();
+    // V2 = V S^T with S = -T and T^{-1} = D + striu(V^T V), D = diag(1/tau)  (equivalent to the
+    // recurrence of svd_parallel.h:97-113, but off the per-column critical path): every row x of V2
+    // solves  x (D + U)^T = -v  by back substitution, in place over the row of V held in Ps.
+    for (int rl = tid; rl < R; rl += nt) {
+        const int row = r0 + rl;
+        T* x = Ps + rl * ld;
+        const int khi = min(kmax - 1, row);
+        for (int c = b - 1; c > khi; --c) x[c] = (T)0;
+        for (int c = khi; c >= 0; --c) {
+            T acc = (row == c) ? (T)-1 : -x[c];          // -v[c]
+            for (int k = c + 1; k <= khi; ++k) acc -= x[k] * Gm[c * b + k];
+            x[c] = acc * taus[c];
         }
     }
-    if (g == 0) for (int e = tid; e < b * b; e += nt) S_out[e] = Ss[e];
+    __syncthreads();
+    if (!kTrans) {
+        if (in2d)
+            for (int rl = tyy; rl < R; rl += rgroups) V2[(size_t)(r0 + rl) * b + tx] = Ps[rl * ld + tx];
+    } else {
+        for (int c = wrp; c < b; c += nwarps)
+            for (int rl = lane; rl < R; rl += 32) V2[(size_t)c * m + (r0 + rl)] = Ps[rl * ld + c];
+    }
+    // S itself (b x b, upper triangular) is only needed by callers that ask for it: CTA 0 rebuilds it
+    // from the Gram matrix with the reference recurrence S[0:j,j] = -tau_j S[0:j,0:j] g_j, S[j][j] = -tau_j.
+    if (g == 0 && S_out != nullptr) {
+        __syncthreads();
+        T* Ss = psum;                                     // reuse: needs b*b <= blockDim only for small b
+        (void)Ss;
+        if (tid == 0) {
+            for (int j = 0; j < kmax; ++j) {
+                for (int r = 0; r < j; ++r) {
+                    T acc = (T)0;
+                    for (int c = r; c < j; ++c) acc += S_out[r * b + c] * Gm[c * b + j];
+                    S_out[r * b + j] = -taus[j] * acc;
+                }
+                S_out[j * b + j] = -taus[j];
+                for (int r = j + 1; r < b; ++r) S_out[r * b + j] = (T)0;
+            }
+        }
+    }
     // no CTA may exit while a peer can still read its shared memory
     if (kCluster) cg::this_cluster().sync();
 }
@@ -210,7 +236,7 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
     T* V = reinterpret_cast<T*>(c->v);
     T* V2 = reinterpret_cast<T*>(c->v2);
-    T* S = reinterpret_cast<T*>(c->s);
+    T* S = nullptr;      // the compact-WY factor itself is not needed: V2 = V S^T is produced directly
     T* red = reinterpret_cast<T*>(c->red);
     unsigned* bar = c->bar;
     // ---- cluster transport when the panel fits the shared memory of one cluster ---------------------

@@ -37,6 +37,18 @@ __host__ __device__ inline int stage2_threads(int c) {
     return ((need + 31) / 32) * 32;
 }
 
+// Poll a progress counter with relaxed loads (an acquire load per poll would invalidate the L1
+// every time: CCTL.IVALL), then order the following reads with one acquire fence.
+__device__ __forceinline__ void wait_progress(const int* p, int need) {
+    int v;
+    while (true) {
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= need) break;
+        __nanosleep(20);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 // Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.
 template <typename T>
 __device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* sc) {
@@ -61,15 +73,17 @@ __device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* 
 
 // H = I - tau w w^T exactly as svd_serial.h:199-211 (w_0 = 1, w_i = x_i * alpha).
 template <typename T>
-__device__ __forceinline__ void build_h(const T* x, int xs, int L, const T* sc, T* H, int ldh) {
+__device__ __forceinline__ void build_h(const T* x, int xs, int L, const T* sc, T* H, int ldh, int tx, int ty, int tys) {
     const T alpha = sc[0], mtau = -sc[1];
-    for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-        int i = e / L, j = e - i * L;
-        T wi = (i == 0) ? (T)1 : RN<T>::mul(x[i * xs], alpha);
-        T wj = (j == 0) ? (T)1 : RN<T>::mul(x[j * xs], alpha);
-        T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wi, wj)), mtau);
-        if (i == j) h = RN<T>::add((T)1, h);
-        H[i * ldh + j] = h;
+    if (tx < L) {
+        const int j = tx;
+        const T wj = (j == 0) ? (T)1 : RN<T>::mul(x[j * xs], alpha);
+        for (int i = ty; i < L; i += tys) {
+            T wi = (i == 0) ? (T)1 : RN<T>::mul(x[i * xs], alpha);
+            T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wi, wj)), mtau);
+            if (i == j) h = RN<T>::add((T)1, h);
+            H[i * ldh + j] = h;
+        }
     }
 }
 
@@ -90,7 +104,25 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
 #pragma unroll
     for (int q = 0; q < kTileR; ++q) xr[q] = min(ry + q * RT, nr - 1) * ldx;
     const int y0 = min(cx, nc - 1), y1 = min(cx + CT, nc - 1);
-    for (int k = 0; k < L; ++k) {
+    int k = 0;
+    for (; k + 4 <= L; k += 4) {               // operands of 4 steps are fetched before they are consumed
+        T yv[4][2], xv[4][kTileR];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            yv[u][0] = Y[(k + u) * ldy + y0];
+            yv[u][1] = Y[(k + u) * ldy + y1];
+#pragma unroll
+            for (int q = 0; q < kTileR; ++q) xv[u][q] = X[xr[q] + k + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < kTileR; ++q) {
+                acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
+                acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
+            }
+    }
+    for (; k < L; ++k) {
         const T yv0 = Y[k * ldy + y0], yv1 = Y[k * ldy + y1];
 #pragma unroll
         for (int q = 0; q < kTileR; ++q) {
@@ -109,8 +141,8 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
+template <typename T, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = band, w = band + 1;
     const int ldr = c + 1, ldl = 2 * c + 1, ldh = c + 1;
@@ -120,6 +152,7 @@ __global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A
     T* sc = H + c * ldh;                        // alpha, tau
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t N = (size_t)n;
+    const int tx = tid % c, ty = tid / c, tys = nt / c;   // 2-D view of the CTA: c columns x tys rows (nt >= c)
 
     for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
         const int top_j2 = min(i + 2 * w - 1, n);
@@ -133,7 +166,7 @@ __global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A
             {
                 const int q = 2 * p;
                 if (i > 0) {
-                    if (tid == 0) while (ld_acquire(&prog[i - 1]) < q + 4) __nanosleep(20);
+                    if (tid == 0) wait_progress(&prog[i - 1], q + 4);
                     __syncthreads();
                 }
                 const int nc = r2 - r1, nr = r2 - r0;
@@ -147,18 +180,18 @@ __global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A
                 } else {                          // issue the fetch of N, consume it after H is built
 #pragma unroll
                     for (int u = 0; u < kNewPerThread; ++u) {
-                        int e = tid + u * nt;
-                        if (e < newcnt) nv[u] = ld_cg(&A[(size_t)(r0 + have + e / nc) * N + (r1 + e % nc)]);
+                        int r = ty + u * tys;
+                        if (r < nr - have && tx < nc) nv[u] = ld_cg(&A[(size_t)(r0 + have + r) * N + (r1 + tx)]);
                     }
                 }
                 if (tid == 0) reflector_scalars<T>(WR, 1, nc, sc);
                 __syncthreads();
-                build_h<T>(WR, 1, nc, sc, H, ldh);
+                build_h<T>(WR, 1, nc, sc, H, ldh, tx, ty, tys);
                 if (have != 0) {
 #pragma unroll
                     for (int u = 0; u < kNewPerThread; ++u) {
-                        int e = tid + u * nt;
-                        if (e < newcnt) WR[(have + e / nc) * ldr + e % nc] = nv[u];
+                        int r = ty + u * tys;
+                        if (r < nr - have && tx < nc) WR[(have + r) * ldr + tx] = nv[u];
                     }
                 }
                 __syncthreads();
@@ -178,24 +211,23 @@ __global__ void __launch_bounds__(1024, 1) stage2_chase_kernel(T* __restrict__ A
             {
                 const int q = 2 * p + 1;
                 if (i > 0) {
-                    if (tid == 0) while (ld_acquire(&prog[i - 1]) < q + 4) __nanosleep(20);
+                    if (tid == 0) wait_progress(&prog[i - 1], q + 4);
                     __syncthreads();
                 }
                 const int nr = r2 - r1, fc = r2 - r1, nc = fc + nn;
                 T nv[kNewPerThread];
-                const int newcnt = nr * nn;
 #pragma unroll
                 for (int u = 0; u < kNewPerThread; ++u) {
-                    int e = tid + u * nt;
-                    if (e < newcnt) nv[u] = ld_cg(&A[(size_t)(r1 + e / nn) * N + (r2 + e % nn)]);
+                    int r = ty + u * tys;
+                    if (r < nr && tx < nn) nv[u] = ld_cg(&A[(size_t)(r1 + r) * N + (r2 + tx)]);
                 }
                 if (tid == 0) reflector_scalars<T>(WL, ldl, nr, sc);
                 __syncthreads();
-                build_h<T>(WL, ldl, nr, sc, H, ldh);
+                build_h<T>(WL, ldl, nr, sc, H, ldh, tx, ty, tys);
 #pragma unroll
                 for (int u = 0; u < kNewPerThread; ++u) {
-                    int e = tid + u * nt;
-                    if (e < newcnt) WL[(e / nn) * ldl + fc + e % nn] = nv[u];
+                    int r = ty + u * tys;
+                    if (r < nr && tx < nn) WL[r * ldl + fc + tx] = nv[u];
                 }
                 __syncthreads();
                 // cols [r1,r2) are finished; cols [r2,c3) become the top block of RIGHT(p+1)
@@ -236,7 +268,8 @@ int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) {
     if (nt > 1024) return SVDB200_E_CAPACITY;      // band <= 64
     if (cb * cb > kNewPerThread * nt) return SVDB200_E_CAPACITY;
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
-    auto kern = stage2_chase_kernel<T>;
+    // small bands run with <= 256 threads: instantiate that case without the 64-register cap
+    auto kern = nt <= 256 ? stage2_chase_kernel<T, 256> : stage2_chase_kernel<T, 1024>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVDB_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
