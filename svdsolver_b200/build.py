@@ -25,7 +25,8 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "svdb200.h")]
+    deps = [os.path.join(dp, f) for dp, _, fs in os.walk(CSRC) for f in fs]
+    deps += [os.path.join(HERE, "..", "include", f) for f in ("svdb200.h", "svdb200_matrix.hpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -51,7 +52,20 @@ def build(force=False, verbose=False, extra=()):
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    build_cli()
     return LIB
+
+
+CLI = os.path.join(HERE, "bin", "svd_b200")
+
+
+def build_cli():
+    """Host-only C++ driver (reference CLI contract) over include/svdb200_matrix.hpp + libsvdb200.so."""
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(HERE, "..", "include"),
+                           os.path.join(CSRC, "cli", "svd_b200.cpp"), "-o", CLI,
+                           "-L", HERE, "-lsvdb200", "-Wl,-rpath,$ORIGIN/.."])
+    return CLI
 
 
 if __name__ == "__main__":

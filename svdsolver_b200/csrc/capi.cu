@@ -222,8 +222,14 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 }
 
 // Host-pointer chain with per-stage CUDA-event timing.  what: bit0 stage1, bit1 stage2, bit2 qr.
+int ensure_staging(Ctx* c) {
+    if (!c->a_dev) SVDB_CHECK(c, cudaMalloc(&c->a_dev, c->esz * c->max_n * c->max_n));
+    return 0;
+}
+
 template <typename T>
 int host_chain(Ctx* c, T* a, size_t n, size_t band, int order, int what, T* d, T* e, T* sigma, long long* sweeps) {
+    if (what & 3) SVDB_TRY(ensure_staging(c));
     T* ad = reinterpret_cast<T*>(c->a_dev);
     T* dd = reinterpret_cast<T*>(c->d);
     T* ed = reinterpret_cast<T*>(c->e);
@@ -327,7 +333,7 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     for (auto& e : c->ev) SVDB_CREATE_CHECK(cudaEventCreate(&e));
     for (auto& e : c->pev) SVDB_CREATE_CHECK(cudaEventCreate(&e));
     const size_t es = c->esz, nb = round_up(max_n, 128) + 128;
-    SVDB_CREATE_CHECK(cudaMalloc(&c->a_dev, es * max_n * max_n));
+    // a_dev (max_n^2 staging for the host-pointer entry points) is allocated on first use
     SVDB_CREATE_CHECK(cudaMalloc(&c->v, es * nb * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->v2, es * nb * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->w, es * nb * band));
@@ -484,6 +490,7 @@ int svdb200_synchronize(svdb200_handle h) {
         SVDB_ENTER(T)                                                                                                    \
         if (!a || !b || !out || n == 0 || band == 0) return SVDB200_E_ARG;                                               \
         if (n > c->max_n) return SVDB200_E_CAPACITY;                                                                     \
+        SVDB_TRY(ensure_staging(c));                                                                                     \
         T* ad = reinterpret_cast<T*>(c->a_dev);                                                                          \
         T* bd = nullptr;                                                                                                 \
         SVDB_CHECK(c, cudaMalloc(&bd, sizeof(T) * n * n));                                                               \

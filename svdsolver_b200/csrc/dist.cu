@@ -1,19 +1,293 @@
-// Multi-GPU stage 1 (1-D block-cyclic over columns, NCCL panel broadcast) -- see dist_impl notes
-// in DESIGN.md.  NCCL is bound at run time with dlopen so that the single-GPU entry points carry
-// no link-time dependency on libnccl.
+// Multi-GPU stage 1 (BASELINE config 4): dense -> band with the matrix distributed 1-D
+// block-cyclically over COLUMNS (block = band), one process per GPU, NCCL over NVLink/NVSwitch.
+// The reference has no multi-GPU path; the single-GPU panel order
+// (cuda_brd_p1, svd_cuda_2.cu:1117) is distributed as follows, per block step k:
+//   QR half-step : the owner of block column k factorises the full-height panel locally
+//                  (all rows are local under a column distribution) and ncclBroadcast()s
+//                  [V | V S^T] (2*m*b elements); every rank updates its local trailing columns
+//                  with the same two GEMMs as the single-GPU path.
+//   LQ half-step : the b x n' row panel spans all ranks: ncclAllGather of the local pieces
+//                  (b*n' elements in total), every rank factorises the SAME assembled panel
+//                  redundantly (deterministic kernel => identical U on every rank, no broadcast),
+//                  W = A U^T is a sum over the column distribution: local partial product +
+//                  ncclAllReduce(sum) of m' x b, then the local rank-b update.
+// Traffic per block step is O(n*b) elements against O(n^2*b/P) flops per rank.
+// NCCL is bound at run time (dlopen), so the single-GPU library has no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <new>
 #include "common.cuh"
 
+namespace svdb200 {
+template <typename T, bool kTrans> int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b);
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.lib) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+#define SVDB_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+    SVDB_SYM(GetUniqueId, "ncclGetUniqueId");
+    SVDB_SYM(CommInitRank, "ncclCommInitRank");
+    SVDB_SYM(CommDestroy, "ncclCommDestroy");
+    SVDB_SYM(Broadcast, "ncclBroadcast");
+    SVDB_SYM(AllGather, "ncclAllGather");
+    SVDB_SYM(AllReduce, "ncclAllReduce");
+    SVDB_SYM(GetErrorString, "ncclGetErrorString");
+#undef SVDB_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.AllGather && api.AllReduce;
+    return api;
+}
+
+struct Dist {
+    Ctx* ctx = nullptr;          // workspace + stream (created through svdb200_create)
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    size_t n = 0, band = 0;
+    void* rowpanel = nullptr;    // band x n   : assembled LQ row panel (global column order)
+    void* gather = nullptr;      // nranks x band x ncl_max : all-gather landing zone
+    void* sendbuf = nullptr;     // band x ncl_max
+    void* ut_loc = nullptr;      // ncl_max x band
+    void* u2_loc = nullptr;      // band x ncl_max
+    size_t ncl_max = 0;
+};
+
+#define SVDB_NCCL(d, expr)                                                           \
+    do {                                                                             \
+        ncclResult_t _r = (expr);                                                    \
+        if (_r != ncclSuccess) {                                                     \
+            (d)->ctx->last_error = std::string(#expr) + ": " +                       \
+                                   (nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error"); \
+            return SVDB200_NCCL_ERR + (int)_r;                                       \
+        }                                                                            \
+    } while (0)
+
+template <typename T> ncclDataType_t nccl_type();
+template <> ncclDataType_t nccl_type<float>() { return ncclFloat32; }
+template <> ncclDataType_t nccl_type<double>() { return ncclFloat64; }
+
+// local block lb of rank r holds global block lb * P + r
+__host__ __device__ inline size_t first_local_block_after(size_t k, int r, int P) {
+    // number of local blocks with global index <= k
+    return k >= (size_t)r ? (k - r) / P + 1 : 0;
+}
+
+// pack rows [0,b) x local cols [c0, c0+ncl) (ld = ldl) into a contiguous b x ncl_max buffer
+template <typename T>
+__global__ void pack_rows_kernel(const T* __restrict__ a, size_t ldl, int b, size_t ncl, size_t ncl_max, T* __restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)b * ncl_max) return;
+    size_t r = e / ncl_max, c = e % ncl_max;
+    out[e] = c < ncl ? a[r * ldl + c] : (T)0;
+}
+// gathered [rank][b][ncl_max] -> row panel b x np in global column order.
+// Global trailing block t (0-based among the trailing blocks, global block index k+1+t) lives on
+// rank (k+1+t) % P at position (its local block index) - (first local trailing block of that rank).
+template <typename T>
+__global__ void assemble_panel_kernel(const T* __restrict__ gathered, int b, size_t np, size_t ncl_max, size_t k, int P,
+                                      T* __restrict__ panel) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)b * np) return;
+    size_t r = e / np, gc = e % np;
+    size_t t = gc / b, within = gc % b;
+    size_t gblock = k + 1 + t;
+    int owner = (int)(gblock % P);
+    size_t lb = gblock / P, lb0 = first_local_block_after(k, owner, P);
+    size_t lc = (lb - lb0) * b + within;
+    panel[r * np + gc] = gathered[((size_t)owner * b + r) * ncl_max + lc];
+}
+// local slices of the factored panel / reflectors for this rank:
+//   a rows [0,b) x local trailing cols  <- panel columns owned by this rank
+//   ut_loc (ncl x b) <- Ut (np x b) rows owned ; u2_loc (b x ncl) <- U2 (b x np) columns owned
+template <typename T>
+__global__ void scatter_local_kernel(const T* __restrict__ panel, const T* __restrict__ ut, const T* __restrict__ u2, int b, size_t np,
+                                     size_t ncl, size_t k, int rank, int P, T* __restrict__ a, size_t ldl, T* __restrict__ ut_loc,
+                                     T* __restrict__ u2_loc) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)b * ncl) return;
+    size_t r = e / ncl, lc = e % ncl;
+    size_t lb0 = first_local_block_after(k, rank, P);
+    size_t gblock = (lb0 + lc / b) * P + rank;
+    size_t gc = (gblock - (k + 1)) * b + lc % b;
+    a[r * ldl + lc] = panel[r * np + gc];
+    u2_loc[r * ncl + lc] = u2[r * np + gc];
+    ut_loc[lc * b + r] = ut[gc * b + r];
+}
+
+template <typename T>
+int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
+    Ctx* c = d->ctx;
+    const int P = d->nranks, rk = d->rank, b = (int)band;
+    const size_t nb = n / band;
+    const size_t ldl = svdb200_dist_local_cols(n, band, rk, P);
+    T* V = reinterpret_cast<T*>(c->v);
+    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* W = reinterpret_cast<T*>(c->w);
+    T* rowpanel = reinterpret_cast<T*>(d->rowpanel);
+    T* gathered = reinterpret_cast<T*>(d->gather);
+    T* sendbuf = reinterpret_cast<T*>(d->sendbuf);
+    T* ut_loc = reinterpret_cast<T*>(d->ut_loc);
+    T* u2_loc = reinterpret_cast<T*>(d->u2_loc);
+    cudaStream_t s = c->stream;
+    for (size_t k = 0; k < nb; ++k) {
+        const size_t o = k * band, m = n - o;
+        const int owner = (int)(k % P);
+        const size_t lb_panel = k / P;
+        // ---- QR half-step ------------------------------------------------------------------------------
+        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + lb_panel * band, ldl, (int)m, b)));
+        if (P > 1) {
+            // V and V2 are adjacent allocations only by accident: broadcast them separately
+            SVDB_NCCL(d, nccl().Broadcast(V, V, m * band, nccl_type<T>(), owner, d->comm, s));
+            SVDB_NCCL(d, nccl().Broadcast(V2, V2, m * band, nccl_type<T>(), owner, d->comm, s));
+        }
+        const size_t lb0 = first_local_block_after(k, rk, P);        // first local block with global index > k
+        const size_t ncl = ldl - lb0 * band;                         // local trailing columns
+        if (ncl > 0) {
+            T* A2 = a + o * ldl + lb0 * band;
+            SVDB_TRY(gemm_tn<T>(c, V, A2, ldl, m, ncl, band, W));
+            SVDB_TRY(rank_update<T>(c, A2, ldl, m, ncl, band, V2, W, ncl));
+        }
+        // ---- LQ half-step ------------------------------------------------------------------------------
+        if (o + band < n - 1) {
+            const size_t np = n - o - band;                          // global width of the row panel
+            const size_t mr = m - band;
+            // gather the b x np row panel on every rank
+            {
+                size_t cnt = (size_t)b * d->ncl_max;
+                pack_rows_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(a + o * ldl + lb0 * band, ldl, b, ncl, d->ncl_max, sendbuf);
+                c->launches++;
+                if (P > 1) SVDB_NCCL(d, nccl().AllGather(sendbuf, gathered, cnt, nccl_type<T>(), d->comm, s));
+                else SVDB_CHECK(c, cudaMemcpyAsync(gathered, sendbuf, cnt * sizeof(T), cudaMemcpyDeviceToDevice, s));
+                size_t tot = (size_t)b * np;
+                assemble_panel_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(gathered, b, np, d->ncl_max, k, P, rowpanel);
+                c->launches++;
+            }
+            // every rank factorises the same panel: Ut (np x b) -> c->v, U2 (b x np) -> c->v2
+            SVDB_TRY((launch_panel_public<T, true>(c, rowpanel, np, (int)np, b)));
+            if (ncl > 0) {
+                size_t cnt = (size_t)b * ncl;
+                scatter_local_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(rowpanel, V, V2, b, np, ncl, k, rk, P,
+                                                                                       a + o * ldl + lb0 * band, ldl, ut_loc, u2_loc);
+                c->launches++;
+            }
+            if (mr > 0) {
+                T* A3 = a + (o + band) * ldl + lb0 * band;
+                if (ncl > 0) SVDB_TRY(gemm_nn<T>(c, A3, ldl, mr, ncl, band, ut_loc, W));
+                else SVDB_CHECK(c, cudaMemsetAsync(W, 0, mr * band * sizeof(T), s));
+                if (P > 1) SVDB_NCCL(d, nccl().AllReduce(W, W, mr * band, nccl_type<T>(), ncclSum, d->comm, s));
+                if (ncl > 0) SVDB_TRY(rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl));
+            }
+        }
+    }
+    SVDB_CHECK(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+}  // namespace svdb200
+
+using namespace svdb200;
+
 extern "C" {
-int svdb200_dist_unique_id(void*) { return SVDB200_E_STATE; }
-int svdb200_dist_create(svdb200_dist_handle*, int, int, int, const void*, size_t, size_t, int) { return SVDB200_E_STATE; }
-int svdb200_dist_destroy(svdb200_dist_handle) { return SVDB200_E_STATE; }
+
 size_t svdb200_dist_local_cols(size_t n, size_t band, int rank, int nranks) {
-    if (band == 0 || nranks <= 0 || n % band != 0) return 0;
+    if (band == 0 || nranks <= 0 || n % band != 0 || rank < 0 || rank >= nranks) return 0;
     size_t nb = n / band, mine = nb / nranks + ((size_t)rank < nb % nranks ? 1 : 0);
     return mine * band;
 }
-int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle, float*, size_t, size_t) { return SVDB200_E_STATE; }
-int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle, double*, size_t, size_t) { return SVDB200_E_STATE; }
-int svdb200_dist_set_stream(svdb200_dist_handle, void*) { return SVDB200_E_STATE; }
-long long svdb200_dist_launch_count(svdb200_dist_handle) { return -1; }
+
+int svdb200_dist_unique_id(void* out128) {
+    if (!out128) return SVDB200_E_ARG;
+    if (!nccl().ok) return SVDB200_E_STATE;
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) return SVDB200_NCCL_ERR + (int)r;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, 128);
+    return 0;
 }
+
+int svdb200_dist_create(svdb200_dist_handle* out, int device, int rank, int nranks, const void* nccl_unique_id, size_t n, size_t band,
+                        int dtype) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return SVDB200_E_ARG;
+    if (band == 0 || n == 0 || n % band != 0) return SVDB200_E_SHAPE;
+    if (nranks > 1 && (!nccl_unique_id || !nccl().ok)) return SVDB200_E_STATE;
+    Dist* d = new (std::nothrow) Dist();
+    if (!d) return SVDB200_E_STATE;
+    svdb200_handle h = nullptr;
+    int st = svdb200_create(&h, device, n, band, dtype);
+    if (st != 0) { delete d; return st; }
+    d->ctx = reinterpret_cast<Ctx*>(h);
+    d->rank = rank; d->nranks = nranks; d->n = n; d->band = band;
+    const size_t es = d->ctx->esz;
+    d->ncl_max = (n / band + nranks - 1) / nranks * band;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&d->rowpanel, es * band * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d->gather, es * (size_t)nranks * band * d->ncl_max);
+    if (e == cudaSuccess) e = cudaMalloc(&d->sendbuf, es * band * d->ncl_max);
+    if (e == cudaSuccess) e = cudaMalloc(&d->ut_loc, es * band * d->ncl_max);
+    if (e == cudaSuccess) e = cudaMalloc(&d->u2_loc, es * band * d->ncl_max);
+    if (e != cudaSuccess) { int s2 = cuda_status(d->ctx, e, "cudaMalloc(dist)"); svdb200_dist_destroy(reinterpret_cast<svdb200_dist_handle>(d)); return s2; }
+    if (nranks > 1) {
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id, 128);
+        ncclResult_t r = nccl().CommInitRank(&d->comm, nranks, id, rank);
+        if (r != ncclSuccess) { svdb200_dist_destroy(reinterpret_cast<svdb200_dist_handle>(d)); return SVDB200_NCCL_ERR + (int)r; }
+    }
+    *out = reinterpret_cast<svdb200_dist_handle>(d);
+    return 0;
+}
+
+int svdb200_dist_destroy(svdb200_dist_handle h) {
+    if (!h) return SVDB200_E_ARG;
+    Dist* d = reinterpret_cast<Dist*>(h);
+    if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
+    if (d->comm) nccl().CommDestroy(d->comm);
+    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (d->ctx) svdb200_destroy(reinterpret_cast<svdb200_handle>(d->ctx));
+    delete d;
+    return 0;
+}
+
+int svdb200_dist_set_stream(svdb200_dist_handle h, void* stream) {
+    if (!h) return SVDB200_E_ARG;
+    return svdb200_set_stream(reinterpret_cast<svdb200_handle>(reinterpret_cast<Dist*>(h)->ctx), stream);
+}
+
+long long svdb200_dist_launch_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->ctx->launches : -1; }
+
+int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle h, float* a, size_t n, size_t band) {
+    if (!h || !a) return SVDB200_E_ARG;
+    Dist* d = reinterpret_cast<Dist*>(h);
+    if (d->ctx->dtype != SVDB200_F32 || n != d->n || band != d->band) return SVDB200_E_ARG;
+    SVDB_CHECK(d->ctx, cudaSetDevice(d->ctx->device));
+    return dist_stage1<float>(d, a, n, band);
+}
+int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle h, double* a, size_t n, size_t band) {
+    if (!h || !a) return SVDB200_E_ARG;
+    Dist* d = reinterpret_cast<Dist*>(h);
+    if (d->ctx->dtype != SVDB200_F64 || n != d->n || band != d->band) return SVDB200_E_ARG;
+    SVDB_CHECK(d->ctx, cudaSetDevice(d->ctx->device));
+    return dist_stage1<double>(d, a, n, band);
+}
+
+}  // extern "C"

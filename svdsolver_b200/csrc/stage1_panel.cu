@@ -293,6 +293,14 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
 
 }  // namespace
 
+// panel factorisation for other translation units (the multi-GPU driver in dist.cu)
+template <typename T, bool kTrans>
+int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b) { return launch_panel<T, kTrans>(c, a, lda, m, b); }
+template int launch_panel_public<float, false>(Ctx*, float*, size_t, int, int);
+template int launch_panel_public<float, true>(Ctx*, float*, size_t, int, int);
+template int launch_panel_public<double, false>(Ctx*, double*, size_t, int, int);
+template int launch_panel_public<double, true>(Ctx*, double*, size_t, int, int);
+
 // Driver: same panel sequence as svd_cpu.h:382-423 / svd_cuda_2.cu:1148-1213.
 template <typename T>
 int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {

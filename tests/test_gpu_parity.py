@@ -255,3 +255,24 @@ def test_error_statuses(capi):
         with pytest.raises(capi.SvdB200Error) as ei:
             h.dense_to_band(np.zeros((8, 12)), 4)
         assert ei.value.status == -2
+
+
+# ------------------------------------------------------------------ multi-GPU driver, 1 rank -------
+@pytest.mark.parametrize("suf,n,b", [("f64", 512, 32), ("f32", 384, 64), ("f64", 256, 4)])
+def test_dist_driver_single_rank_equals_panel_order(capi, suf, n, b):
+    """The block-cyclic driver on ONE rank runs the same kernels as the single-GPU panel order."""
+    import ctypes
+    import torch
+    from svdsolver_b200 import distributed as D
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    with handle(capi, n, b, suf) as h:
+        ref = h.dense_to_band(a, b, capi.ORDER_PANEL)
+    loc = torch.from_numpy(a.copy()).cuda()
+    torch.cuda.synchronize()
+    with D.DistHandle(n, b, DT[suf], 0, 1, (ctypes.c_ubyte * 128)()) as dh:
+        dh.dense_to_band_dev(loc.data_ptr())
+        torch.cuda.synchronize()
+        assert dh.launch_count() > 0
+    out = loc.cpu().numpy()
+    assert band_rel(out, ref, b) <= TOL[suf]
+    assert np.abs(np.tril(out, -1)).max() == 0
