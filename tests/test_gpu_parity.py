@@ -276,3 +276,22 @@ def test_dist_driver_single_rank_equals_panel_order(capi, suf, n, b):
     out = loc.cpu().numpy()
     assert band_rel(out, ref, b) <= TOL[suf]
     assert np.abs(np.tril(out, -1)).max() == 0
+
+
+# ------------------------------------------------------------------ CLI (reference `check` mode) ----
+@pytest.mark.parametrize("tname", ["float", "double"])
+def test_cli_check_mode(capi, tname):
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "svdsolver_b200", "bin", "svd_b200")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    out = subprocess.run([exe, "check", "64", GOLDEN, tname], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0
+    txt = out.stdout
+    import re
+    mse_tile = float(re.search(r"tile order = parallel::brd_p1\): ([0-9.eE+-]+)", txt).group(1))
+    mse_bid = float(re.search(r"MSE of Bidiagonal Reduction: ([0-9.eE+-]+)", txt).group(1))
+    assert mse_tile == 0.0 and mse_bid == 0.0          # bit-exact against band_* / bidiagonal_*
+    mse_panel = float(re.search(r"MSE of Band Reduction: ([0-9.eE+-]+)", txt).group(1))
+    assert mse_panel < (1e-3 if tname == "float" else 1e-9)

@@ -157,3 +157,30 @@ def test_compiled_reference_agrees_when_present(oracle, refso):
     assert np.array_equal(oracle.brd_p1(a, 8), r)
     refso.svdref_brd_p2_f64(r.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(80), ctypes.c_size_t(8), None, None)
     assert np.array_equal(oracle.brd_p2(oracle.brd_p1(a, 8), 8)[0], r)
+
+
+@pytest.mark.parametrize("n,b", [(64, 4), (65, 4), (100, 7), (96, 32), (130, 16), (33, 32)])
+def test_stage2_cross_sweep_dependency_lag(n, b):
+    """The pipelining rule of csrc/stage2_chase.cu: with ops numbered RIGHT(p)=2p, LEFT(p)=2p+1, op q
+    of sweep i+1 overlaps ops of sweep i only up to index q+3 (so it may start after q+4 ops)."""
+    c, w = b, b + 1
+
+    def ops(i):
+        out = [(i, min(i + w, n), i + 1, min(i + w, n)), (i + 1, min(i + w, n), i + 1, min(i + 2 * w - 1, n))]
+        for k in range((n - min(i + 2 * w - 1, n)) // c + 1):
+            r0, r1, r2, c3 = (min(i + 1 + (k + j) * c, n) for j in range(4))
+            out.append((r0, r2, r1, r2) if r2 > r1 else None)
+            out.append((r1, r2, r1, c3) if c3 > r1 else None)
+        return out
+
+    def overlap(a, bb):
+        return a and bb and a[0] < bb[1] and bb[0] < a[1] and a[2] < bb[3] and bb[2] < a[3]
+
+    worst = 0
+    for i in range(n - 2):
+        A, B = ops(i), ops(i + 1)
+        for q, ob in enumerate(B):
+            for qa, oa in enumerate(A):
+                if overlap(oa, ob):
+                    worst = max(worst, qa - q)
+    assert worst <= 3
