@@ -1,5 +1,6 @@
 // C ABI of libsvdb200.so (declared in include/svdb200.h).  Thin: argument checks, workspace
 // ownership, host<->device staging and CUDA-event timing; all arithmetic lives in the kernels.
+#include <cstdlib>
 #include <new>
 #include "common.cuh"
 
@@ -336,6 +337,16 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     // a_dev (max_n^2 staging for the host-pointer entry points) is allocated on first use
     SVDB_CREATE_CHECK(cudaMalloc(&c->v, es * nb * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->v2, es * nb * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->vb, es * nb * band));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->v2b, es * nb * band));
+    {
+        int lo = 0, hi = 0;
+        SVDB_CREATE_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SVDB_CREATE_CHECK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+        for (auto& e : c->lev) SVDB_CREATE_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const char* la = getenv("SVDB200_LOOKAHEAD");
+        if (la && la[0] == '0') c->lookahead = 0;
+    }
     SVDB_CREATE_CHECK(cudaMalloc(&c->w, es * nb * band));
     c->wpart_elems = 16 * nb * band;
     if (c->wpart_elems < 4 * nb) c->wpart_elems = 4 * nb;
@@ -363,11 +374,13 @@ int svdb200_destroy(svdb200_handle h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    void* ptrs[] = {c->a_dev, c->v, c->v2, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
+    void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->lev) if (e) cudaEventDestroy(e);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;

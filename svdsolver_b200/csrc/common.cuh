@@ -23,6 +23,10 @@ struct Ctx {
     void* a_dev = nullptr;         // max_n * max_n : staging for host-pointer calls
     void* v = nullptr;             // max_n * band  : V (QR) / U^T (LQ), row-major, unit diagonal explicit
     void* v2 = nullptr;            // max_n * band  : V S^T (QR) ; band * max_n : S U (LQ)
+    void* vb = nullptr; void* v2b = nullptr;   // second reflector pair (LQ panels) for the look-ahead
+    cudaStream_t aux_stream = nullptr;         // high-priority stream the look-ahead panels run on
+    cudaEvent_t lev[4] = {};
+    int lookahead = 1;
     void* w = nullptr;             // band * max_n  : W = V^T A  /  max_n * band : W = A U^T
     void* wpart = nullptr;         // split-K partials
     size_t wpart_elems = 0;

@@ -11,6 +11,12 @@
 #include "common.cuh"
 
 namespace svdb200 {
+
+// pipelined variants (gemm_fast.cu): return 0 when they ran, 1 when their preconditions do not hold
+template <typename T> int rank_update_fast(Ctx*, T*, size_t, int, int, int, const T*, const T*, size_t);
+template <typename T> int gemm_tn_fast(Ctx*, const T*, const T*, size_t, int, int, int, T*, int, int);
+template <typename T> int gemm_nn_fast(Ctx*, const T*, size_t, int, int, int, const T*, T*, int, int);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +285,10 @@ int rank_update(Ctx* c, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b,
     if (mrows == 0 || ncols == 0) return 0;
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     ProfScope ps(c, 3, 2.0 * (double)mrows * (double)ncols * (double)b);
+    {
+        int st = rank_update_fast<T>(c, cm, ldc, (int)mrows, (int)ncols, (int)b, p, q, ldq);
+        if (st != 1) return st;
+    }
     return launch_rank_update<T, 4, 4>(c, cm, ldc, (int)mrows, (int)ncols, (int)b, p, q, ldq);
 }
 
@@ -288,6 +298,21 @@ int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t nc
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
     ProfScope ps(c, 1, 2.0 * (double)mrows * (double)ncols * (double)b);
+    if (B == 32 || B == 64) {          // pipelined kernel: 128-column tiles, 16-row stages
+        long long tiles_f = (N + 127) / 128;
+        int splits_f = pick_splits(tiles_f, (M + KC - 1) / KC, c->num_sms, c->wpart_elems, (size_t)B * N);
+        int rps = (((M + splits_f - 1) / splits_f + KC - 1) / KC) * KC;
+        splits_f = (M + rps - 1) / rps;
+        T* out_f = splits_f == 1 ? w : reinterpret_cast<T*>(c->wpart);
+        int st = gemm_tn_fast<T>(c, v, cm, ldc, M, N, B, out_f, splits_f, rps);
+        if (st == 0 && splits_f > 1) {
+            size_t count = (size_t)B * N;
+            reduce_partials_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(out_f, w, count, splits_f);
+            SVDB_CHECK(c, cudaGetLastError());
+            c->launches++;
+        }
+        if (st != 1) return st;
+    }
     int wm, wn;
     if (B <= 32) { wm = 1; wn = 8; } else if (B <= 64) { wm = 2; wn = 4; } else { wm = 4; wn = 2; }
     const int BMT = wm * 32, BN = wn * 16;
@@ -323,6 +348,21 @@ int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t 
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
     ProfScope ps(c, 2, 2.0 * (double)mrows * (double)ncols * (double)b);
+    if (B == 32 || B == 64) {          // pipelined kernel: 128-row tiles, 32-column stages
+        long long tiles_f = (M + 127) / 128;
+        int splits_f = pick_splits(tiles_f, (N + KC - 1) / KC, c->num_sms, c->wpart_elems, (size_t)M * B);
+        int cps = (((N + splits_f - 1) / splits_f + KC - 1) / KC) * KC;
+        splits_f = (N + cps - 1) / cps;
+        T* out_f = splits_f == 1 ? w : reinterpret_cast<T*>(c->wpart);
+        int st = gemm_nn_fast<T>(c, cm, ldc, M, N, B, ut, out_f, splits_f, cps);
+        if (st == 0 && splits_f > 1) {
+            size_t count = (size_t)M * B;
+            reduce_partials_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(out_f, w, count, splits_f);
+            SVDB_CHECK(c, cudaGetLastError());
+            c->launches++;
+        }
+        if (st != 1) return st;
+    }
     int wm, wn;
     if (B <= 16) { wm = 8; wn = 1; } else if (B <= 32) { wm = 4; wn = 2; } else if (B <= 64) { wm = 2; wn = 4; } else { wm = 1; wn = 8; }
     const int BM = wm * 32, BNB = wn * 16;

@@ -232,10 +232,11 @@ inline size_t panel_smem_bytes(int rows, int b, size_t esz) {
 }
 
 template <typename T, bool kTrans>
-int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
+int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 = nullptr, cudaStream_t stream = nullptr) {
+    if (!stream) stream = c->stream;
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
-    T* V = reinterpret_cast<T*>(c->v);
-    T* V2 = reinterpret_cast<T*>(c->v2);
+    if (!V) V = reinterpret_cast<T*>(c->v);
+    if (!V2) V2 = reinterpret_cast<T*>(c->v2);
     T* S = nullptr;      // the compact-WY factor itself is not needed: V2 = V S^T is produced directly
     T* red = reinterpret_cast<T*>(c->red);
     unsigned* bar = c->bar;
@@ -255,7 +256,7 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
             cfg.gridDim = dim3(G);
             cfg.blockDim = dim3(kPanelThreads);
             cfg.dynamicSmemBytes = smem;
-            cfg.stream = c->stream;
+            cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = G;
@@ -270,7 +271,7 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
             }
             cudaGetLastError();           // cluster shape not schedulable here: use the grid transport
             c->cluster_ok = c->cluster_ok > 8 ? 8 : 0;
-            return launch_panel<T, kTrans>(c, a, lda, m, b);
+            return launch_panel<T, kTrans>(c, a, lda, m, b, V, V2, stream);
         }
     }
     // ---- cooperative-grid transport -----------------------------------------------------------------------
@@ -284,9 +285,9 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
     auto kern = panel_factor_kernel<T, kTrans, false>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), c->stream));
+    SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), stream));
     void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar};
-    SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, c->stream));
+    SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, stream));
     c->launches++;
     return 0;
 }
@@ -295,40 +296,82 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b) {
 
 // panel factorisation for other translation units (the multi-GPU driver in dist.cu)
 template <typename T, bool kTrans>
-int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b) { return launch_panel<T, kTrans>(c, a, lda, m, b); }
+int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b) { return launch_panel<T, kTrans>(c, a, lda, m, b, nullptr, nullptr, nullptr); }
 template int launch_panel_public<float, false>(Ctx*, float*, size_t, int, int);
 template int launch_panel_public<float, true>(Ctx*, float*, size_t, int, int);
 template int launch_panel_public<double, false>(Ctx*, double*, size_t, int, int);
 template int launch_panel_public<double, true>(Ctx*, double*, size_t, int, int);
 
 // Driver: same panel sequence as svd_cpu.h:382-423 / svd_cuda_2.cu:1148-1213.
+//
+// Look-ahead: the rank-b update of a half-step is split so that the part the NEXT panel lives in
+// (its b rows / b columns) is updated first; the next panel is then factorised on a second,
+// high-priority stream while the main stream finishes the (much larger) rest of the update.
+// QR reflectors use (v, v2), LQ reflectors (vb, v2b), so a panel in flight never overwrites
+// reflectors that the concurrent update still reads.  In profiling mode the steps are serialised
+// so that per-kernel-class times stay meaningful.
 template <typename T>
 int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
     if (band == 0 || n == 0 || n % band != 0) return SVDB200_E_SHAPE;
     if (band > (size_t)kMaxBand || n > c->max_n || band > c->band) return SVDB200_E_CAPACITY;
     const int b = (int)band;
-    T* V = reinterpret_cast<T*>(c->v);
-    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* Vq = reinterpret_cast<T*>(c->v);
+    T* V2q = reinterpret_cast<T*>(c->v2);
+    T* Vl = reinterpret_cast<T*>(c->vb);
+    T* V2l = reinterpret_cast<T*>(c->v2b);
     T* W = reinterpret_cast<T*>(c->w);
+    const bool ahead = !c->profile && c->aux_stream != nullptr && c->lookahead;
+    cudaStream_t s0 = c->stream, s1 = ahead ? c->aux_stream : c->stream;
+    if (ahead) {   // the aux stream must see everything enqueued on the main stream so far
+        SVDB_CHECK(c, cudaEventRecord(c->lev[0], s0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(s1, c->lev[0], 0));
+    }
+    // first QR panel
+    SVDB_TRY((launch_panel<T, false>(c, a, n, (int)n, b, Vq, V2q, s1)));
+    if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[1], s1));
     for (size_t k = 0; k < n; k += band) {
         const size_t m = n - k;                 // panel height
         const size_t nc = n - k - band;         // columns right of the QR panel
-        SVDB_TRY((launch_panel<T, false>(c, a + k * n + k, n, (int)m, b)));
+        const bool has_lq = (k + band < n - 1);
+        if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->lev[1], 0));   // QR panel k is done
         if (nc > 0) {
             T* A2 = a + k * n + k + band;
-            SVDB_TRY(gemm_tn<T>(c, V, A2, n, m, nc, band, W));                   // W = V^T A2
-            SVDB_TRY(rank_update<T>(c, A2, n, m, nc, band, V2, W, nc));          // A2 += (V S^T) W
-        }
-        if (k + band < n - 1) {
-            const size_t mr = m - band;         // rows below the LQ row panel
-            SVDB_TRY((launch_panel<T, true>(c, a + k * n + k + band, n, (int)nc, b)));
-            if (mr > 0) {
-                T* A3 = a + (k + band) * n + k + band;
-                SVDB_TRY(gemm_nn<T>(c, A3, n, mr, nc, band, V, W));              // W = A3 U^T
-                SVDB_TRY(rank_update<T>(c, A3, n, mr, nc, band, W, V2, nc));     // A3 += W (S U)
+            SVDB_TRY(gemm_tn<T>(c, Vq, A2, n, m, nc, band, W));                         // W = V^T A2
+            if (has_lq) {
+                SVDB_TRY(rank_update<T>(c, A2, n, band, nc, band, V2q, W, nc));          // rows of the LQ panel first
+                if (ahead) {
+                    SVDB_CHECK(c, cudaEventRecord(c->lev[2], s0));
+                    SVDB_CHECK(c, cudaStreamWaitEvent(s1, c->lev[2], 0));
+                }
+                SVDB_TRY((launch_panel<T, true>(c, A2, n, (int)nc, b, Vl, V2l, s1)));    // LQ panel (look-ahead)
+                if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[3], s1));
+                if (m > band) SVDB_TRY(rank_update<T>(c, A2 + band * n, n, m - band, nc, band, V2q + band * band, W, nc));
+            } else {
+                SVDB_TRY(rank_update<T>(c, A2, n, m, nc, band, V2q, W, nc));             // A2 += (V S^T) W
             }
         }
+        if (has_lq) {
+            const size_t mr = m - band;         // rows below the LQ row panel
+            if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->lev[3], 0));             // LQ panel is done
+            if (mr > 0) {
+                T* A3 = a + (k + band) * n + k + band;
+                SVDB_TRY(gemm_nn<T>(c, A3, n, mr, nc, band, Vl, W));                     // W = A3 U^T
+                SVDB_TRY(rank_update<T>(c, A3, n, mr, band, band, W, V2l, nc));          // columns of the next QR panel first
+                if (ahead) {
+                    SVDB_CHECK(c, cudaEventRecord(c->lev[2], s0));
+                    SVDB_CHECK(c, cudaStreamWaitEvent(s1, c->lev[2], 0));
+                }
+                SVDB_TRY((launch_panel<T, false>(c, A3, n, (int)mr, b, Vq, V2q, s1)));   // QR panel k+1 (look-ahead)
+                if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[1], s1));
+                if (nc > band) SVDB_TRY(rank_update<T>(c, A3 + band, n, mr, nc - band, band, W, V2l + band, nc));
+            }
+        } else if (nc > 0) {
+            // no LQ for this step (only when the trailing block is a single column): next QR panel directly
+            SVDB_TRY((launch_panel<T, false>(c, a + (k + band) * n + k + band, n, (int)(m - band), b, Vq, V2q, s1)));
+            if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[1], s1));
+        }
     }
+    if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->lev[1], 0));
     return 0;
 }
 

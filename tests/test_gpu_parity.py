@@ -158,7 +158,7 @@ def test_stage1_panel_order_invariants_2048(capi, suf):
 
 # ------------------------------------------------------------------ trailing-update GEMMs ---------
 @pytest.mark.parametrize("suf", ["f32", "f64"])
-@pytest.mark.parametrize("m,n,b", [(256, 192, 32), (300, 130, 64), (64, 60, 4), (1000, 777, 16)])
+@pytest.mark.parametrize("m,n,b", [(256, 192, 32), (300, 130, 64), (64, 60, 4), (1000, 777, 16), (2048, 1536, 64), (1500, 2048, 32)])
 def test_trailing_update_gemms(capi, suf, m, n, b):
     import torch
     dt = torch.float32 if suf == "f32" else torch.float64
