@@ -346,6 +346,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         for (auto& e : c->lev) SVDB_CREATE_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const char* la = getenv("SVDB200_LOOKAHEAD");
         if (la && la[0] == '0') c->lookahead = 0;
+        const char* pr = getenv("SVDB200_PANEL_REG");
+        if (pr && pr[0] == '0') c->panel_reg = 0;
     }
     SVDB_CREATE_CHECK(cudaMalloc(&c->w, es * nb * band));
     c->wpart_elems = 16 * nb * band;

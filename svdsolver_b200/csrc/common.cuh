@@ -27,6 +27,7 @@ struct Ctx {
     cudaStream_t aux_stream = nullptr;         // high-priority stream the look-ahead panels run on
     cudaEvent_t lev[4] = {};
     int lookahead = 1;
+    int panel_reg = 1;             // use the register-resident panel kernel when the shape allows
     void* w = nullptr;             // band * max_n  : W = V^T A  /  max_n * band : W = A U^T
     void* wpart = nullptr;         // split-K partials
     size_t wpart_elems = 0;

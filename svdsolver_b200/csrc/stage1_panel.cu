@@ -27,6 +27,11 @@
 namespace cg = cooperative_groups;
 
 namespace svdb200 {
+
+// register-resident fast path (stage1_panel_reg.cu): 0 = ran, 1 = shape not covered
+template <typename T, bool kTrans>
+int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream, bool cooperative);
+
 namespace {
 
 constexpr int kPanelThreads = 256;
@@ -237,6 +242,12 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
     if (!V) V = reinterpret_cast<T*>(c->v);
     if (!V2) V2 = reinterpret_cast<T*>(c->v2);
+    // register-resident kernel for tall panels (grid transport); cluster-sized panels are issue-bound
+    // either way and stay on the shared-memory kernel below
+    if (c->panel_reg && m > 16 * 256) {
+        int st = launch_panel_reg<T, kTrans>(c, a, lda, m, b, V, V2, stream, stream == c->stream);
+        if (st != 1) return st;
+    }
     T* S = nullptr;      // the compact-WY factor itself is not needed: V2 = V S^T is produced directly
     T* red = reinterpret_cast<T*>(c->red);
     unsigned* bar = c->bar;
