@@ -1,5 +1,6 @@
 // C ABI of libsvdb200.so (declared in include/svdb200.h).  Thin: argument checks, workspace
 // ownership, host<->device staging and CUDA-event timing; all arithmetic lives in the kernels.
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 #include "common.cuh"
@@ -176,16 +177,43 @@ int probe_peak(Ctx* c, int kind, double* tflops) {
     return 0;
 }
 
-// Batched driver, first version: one pipeline instance per matrix on the handle's stream.
+// Batched driver (BASELINE config 5): the matrices are independent, so they are spread round-robin
+// over a pool of sub-handles, each with its own stream and workspace; the small kernels of
+// different matrices overlap on the GPU (a 256 x 256 reduction cannot fill 148 SMs on its own).
+// Shards by matrix across GPUs at the caller's level (one handle per GPU), no collective.
+constexpr int kBatchPool = 16;
+
 template <typename T>
 int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
-    T* d = reinterpret_cast<T*>(c->d);
-    T* e = reinterpret_cast<T*>(c->e);
+    if (count == 0) return 0;
+    if (c->pool_n != n || c->pool_band != band) {
+        for (auto& h : c->pool) if (h) { svdb200_destroy(reinterpret_cast<svdb200_handle>(h)); h = nullptr; }
+        c->pool.clear();
+        for (int i = 0; i < kBatchPool; ++i) {
+            svdb200_handle h = nullptr;
+            int st = svdb200_create(&h, c->device, n, band, c->dtype);
+            if (st != 0) return st;
+            c->pool.push_back(reinterpret_cast<Ctx*>(h));
+        }
+        c->pool_n = n; c->pool_band = band;
+    }
+    const int K = (int)std::min<size_t>(c->pool.size(), count);
+    SVDB_CHECK(c, cudaEventRecord(c->lev[0], c->stream));            // inputs are ready on the caller's stream
+    for (int i = 0; i < K; ++i) SVDB_CHECK(c, cudaStreamWaitEvent(c->pool[i]->stream, c->lev[0], 0));
     for (size_t i = 0; i < count; ++i) {
+        Ctx* s = c->pool[i % K];
         T* ai = a + i * n * n;
-        SVDB_TRY(stage1_panel_order<T>(c, ai, n, band));
-        SVDB_TRY(stage2_chase<T>(c, ai, n, band, d, e));
-        SVDB_TRY(bidiag_qr<T>(c, d, e, n, sigma + i * n));
+        T* d = reinterpret_cast<T*>(s->d);
+        T* e = reinterpret_cast<T*>(s->e);
+        const long long before = s->launches;
+        SVDB_TRY(stage1_panel_order<T>(s, ai, n, band));
+        SVDB_TRY(stage2_chase<T>(s, ai, n, band, d, e));
+        SVDB_TRY(bidiag_qr<T>(s, d, e, n, sigma + i * n));
+        c->launches += s->launches - before;
+    }
+    for (int i = 0; i < K; ++i) {                                    // join
+        SVDB_CHECK(c, cudaEventRecord(c->pool[i]->lev[0], c->pool[i]->stream));
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->stream, c->pool[i]->lev[0], 0));
     }
     return 0;
 }
@@ -376,6 +404,8 @@ int svdb200_destroy(svdb200_handle h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
+    c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "../../include/svdb200.h"
 
 namespace svdb200 {
@@ -53,6 +54,9 @@ struct Ctx {
     double prof_work[SVDB200_PROFILE_CLASSES] = {};
     long long prof_launches[SVDB200_PROFILE_CLASSES] = {};
     cudaEvent_t pev[2] = {};
+    // pool of sub-handles for the batched driver (created on first use for a given n, band)
+    std::vector<Ctx*> pool;
+    size_t pool_n = 0, pool_band = 0;
 };
 
 // Brackets one kernel launch with events when profiling is on (serialises host and device; the

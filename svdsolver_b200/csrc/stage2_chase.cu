@@ -38,7 +38,8 @@ __host__ __device__ inline int stage2_threads(int c) {
 }
 
 // Poll a progress counter with relaxed loads (an acquire load per poll would invalidate the L1
-// every time: CCTL.IVALL), then order the following reads with one acquire fence.
+// every time: CCTL.IVALL), then take ONE acquire load of the same counter to order the reads that
+// follow (cheaper than fence.acq_rel.gpu, which also drains this thread's outstanding stores).
 __device__ __forceinline__ void wait_progress(const int* p, int need) {
     int v;
     while (true) {
@@ -46,7 +47,7 @@ __device__ __forceinline__ void wait_progress(const int* p, int need) {
         if (v >= need) break;
         __nanosleep(20);
     }
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    (void)ld_acquire(p);
 }
 
 // Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.

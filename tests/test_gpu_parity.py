@@ -295,3 +295,17 @@ def test_cli_check_mode(capi, tname):
     assert mse_tile == 0.0 and mse_bid == 0.0          # bit-exact against band_* / bidiagonal_*
     mse_panel = float(re.search(r"MSE of Band Reduction: ([0-9.eE+-]+)", txt).group(1))
     assert mse_panel < (1e-3 if tname == "float" else 1e-9)
+
+
+# ------------------------------------------------------------------ batched (config 5 shape) --------
+@pytest.mark.parametrize("suf,count,n,b", [("f64", 24, 256, 32), ("f32", 10, 128, 16)])
+def test_batched_svdvals(capi, suf, count, n, b):
+    """Many small matrices sharded over the handle's stream pool: sigma == sigma of each matrix's band."""
+    a = np.stack([uniform_matrix(n, n, 586 + i, 0.0, 5.0, DT[suf]) for i in range(count)])
+    with handle(capi, n, b, suf) as h:
+        sig = h.svdvals_batched(a, b)
+        # reference: the same chain, one matrix at a time
+        for i in (0, count // 2, count - 1):
+            s1, _ = h.svdvals(a[i], b)
+            assert np.array_equal(sig[i], s1)
+    assert np.all(np.diff(sig, axis=1) <= 0)
