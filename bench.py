@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="svdb200")
     ap.add_argument("--sizes", default="")           # debugging: comma-separated subset of the sweep
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-n", type=int, default=32768)  # size of the block-cyclic stage-1 measurement (N>1)
     ap.add_argument("--no-big", action="store_true")      # skip the n=16384 trailing-update measurement
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -397,6 +398,45 @@ def main():
     e2e = {"value": world * step_flops * e2e_steps / (tot_ms * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "svdb200_bidiagonalize_{f64,f32} (host pointers, pinned)"}
 
+    # ---- multi-GPU stage 1 (BASELINE config 4 shape): 1-D block-cyclic columns, NCCL panel broadcast ----
+    dist_out = None
+    if world > 1 and not args.no_big:
+        try:
+            from svdsolver_b200 import distributed as D
+            for h in handles.values():
+                h.close()
+            handles = {}
+            del sets, dbuf, ebuf
+            torch.cuda.empty_cache()
+            nd, bd = args.dist_n, 64
+            uid = D.exchange_unique_id(rank, world)
+            ncl = D.local_cols(nd, bd, rank, world)
+            loc = torch.empty(nd, ncl, device=dev, dtype=torch.float32)
+            with D.DistHandle(nd, bd, np.float32, rank, world, uid, device=local_rank) as dh:
+                dh.set_stream(stream.cuda_stream)
+                hfill = capi.Handle(64, 32, np.float32, device=local_rank)
+                hfill.set_stream(stream.cuda_stream)
+                times = []
+                for rep in range(2):
+                    hfill.fill_uniform_dev(loc.data_ptr(), nd * ncl, 586 + nd + 7919 * rank, 0.0, 5.0)
+                    barrier()
+                    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    d0.record(stream)
+                    dh.dense_to_band_dev(loc.data_ptr())
+                    d1.record(stream)
+                    barrier()
+                    t = torch.tensor([d0.elapsed_time(d1)], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    times.append(float(t.item()))
+                hfill.close()
+                tms = min(times)
+                dist_out = {"workload": f"{nd}x{nd} float dense->band, band {bd}, block-cyclic columns over {world} GPUs (BASELINE configs[3] shape)",
+                            "ms": round(tms, 1), "tflops": round(flops(nd) / (tms * 1e-3) * 1e-12, 2), "ranks": world,
+                            "launches_rank0": dh.launch_count(), "collectives": "ncclBroadcast(V|V2), ncclAllGather(row panel), ncclAllReduce(W)"}
+            del loc
+        except Exception as ex:
+            dist_out = {"error": str(ex)}
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,12 +449,13 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_classes_f64": prof_out, "north_star_shape": big, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
+            "kernel_classes_f64": prof_out, "north_star_shape": big, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
         }
         print(json.dumps(line), flush=True)
     for h in handles.values():
         h.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
