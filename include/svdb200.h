@@ -142,8 +142,19 @@ int svdb200_mse_f64(svdb200_handle h, const double* a, const double* b, size_t n
 int svdb200_fill_uniform_dev_f32(svdb200_handle h, float* a_dev, size_t count, unsigned long long seed, double lo, double hi);
 int svdb200_fill_uniform_dev_f64(svdb200_handle h, double* a_dev, size_t count, unsigned long long seed, double lo, double hi);
 /* Register-resident FP64 (DMMA mma.sync m8n8k4 / DFMA) and FP32 (FFMA) peak probes: TFLOP/s. kind:
- * 0 = DFMA, 1 = DMMA f64, 2 = FFMA, 3 = TF32 mma.sync.  Used as roofline denominators. */
+ * 0 = DFMA, 1 = DMMA f64, 2 = FFMA, 3 = TF32 mma.sync, 4 = TF32 tcgen05.mma (M128 N256 K8, operands
+ * resident in shared memory, accumulator in TMEM).  Used as roofline denominators. */
 int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops);
+/* FP32 trailing update on tcgen05/TMEM/TMA (3xTF32).  mode 0: never (mma.sync kernels only), 1: when
+ * the updated block has at least min_elems elements (default), 2: always (tests).  min_elems <= 0
+ * keeps the current threshold.  No effect on FP64 handles (tcgen05.mma has no f64 kind). */
+int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
+/* Unit test of the tcgen05 building blocks (TMA box -> swizzled shared memory -> UMMA descriptors -> TMEM ->
+ * tcgen05.ld): D(128 x 64) = A(128 x 32) B(32 x 64) in one TF32 pass.  a_mn/b_mn select the operand storage:
+ * 0 = K-major (a: 128 x 32 row-major, b: B^T 64 x 32 row-major), 1 = MN-major (a: A^T 32 x 128, b: B 32 x 64).
+ * All device pointers; out has 128*64+1 floats (last = TMEM base address bits), dump 6144 floats = the staged
+ * A (16 KB) and B (8 KB) tiles as they sit in shared memory. */
+int svdb200_tc05_selftest(svdb200_handle h, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);
 
 /* Trailing-update building blocks, exposed for parity tests and kernel-level benchmarks
  * (qr_apply / lq_apply, svd_parallel.h:243-281): all device pointers, row-major.

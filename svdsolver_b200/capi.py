@@ -213,6 +213,10 @@ class Handle:
         self._check(lib().svdb200_last_timings(self.h, *[ctypes.byref(x) for x in v]))
         return dict(zip(("stage1_ms", "stage2_ms", "qr_ms", "h2d_ms", "d2h_ms"), [x.value for x in v]))
 
+    def set_tc05(self, mode, min_elems=0):
+        """FP32 tcgen05/TMEM/TMA trailing update: 0 off, 1 auto (size threshold), 2 always."""
+        self._check(lib().svdb200_set_tc05(self.h, ctypes.c_int(mode), ctypes.c_longlong(min_elems)))
+
     def launch_count(self):
         return int(lib().svdb200_launch_count(self.h))
 

@@ -407,7 +407,7 @@ int svdb200_destroy(svdb200_handle h) {
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
-                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate};
+                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);
@@ -605,10 +605,27 @@ int svdb200_get_profile(svdb200_handle h, double* ms, double* work, long long* l
 long long svdb200_launch_count(svdb200_handle h) { return h ? reinterpret_cast<Ctx*>(h)->launches : -1; }
 
 int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
-    if (!h) return SVDB200_E_ARG;
+    if (!h || !tflops) return SVDB200_E_ARG;
     Ctx* c = reinterpret_cast<Ctx*>(h);
     SVDB_CHECK(c, cudaSetDevice(c->device));
+    if (kind == 4) return probe_tc05_tf32(c, tflops);
     return probe_peak(c, kind, tflops);
+}
+
+int svdb200_tc05_selftest(svdb200_handle h, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump) {
+    if (!h || !a || !b || !out || !dump) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    SVDB_CHECK(c, cudaSetDevice(c->device));
+    return tc05_selftest(c, a_mn, b_mn, a, b, out, dump);
+}
+
+int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems) {
+    if (!h || mode < 0 || mode > 2) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->use_tc05 = mode;
+    if (min_elems > 0) c->tc05_min_elems = min_elems;
+    for (auto* s : c->pool) if (s) { s->use_tc05 = mode; if (min_elems > 0) s->tc05_min_elems = min_elems; }
+    return 0;
 }
 
 }  // extern "C"

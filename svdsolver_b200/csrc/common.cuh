@@ -57,6 +57,11 @@ struct Ctx {
     // pool of sub-handles for the batched driver (created on first use for a given n, band)
     std::vector<Ctx*> pool;
     size_t pool_n = 0, pool_band = 0;
+    // tcgen05 FP32 path (gemm_tc05.cu): hi/lo split scratch for the O(n b) operands, allocated on first use
+    void* tcsplit = nullptr;
+    size_t tcsplit_elems = 0;
+    int use_tc05 = 1;                       // 0 off, 1 when the update is large enough, 2 always (tests)
+    long long tc05_min_elems = 1LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
 };
 
 // Brackets one kernel launch with events when profiling is on (serialises host and device; the
@@ -172,5 +177,7 @@ template <typename T> int fill_uniform(Ctx* c, T* a, size_t count, unsigned long
 template <typename T> int mse_metric(Ctx* c, const T* a, const T* b, size_t n, size_t band, T* out_host);
 template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma);
 int probe_peak(Ctx* c, int kind, double* tflops);
+int probe_tc05_tf32(Ctx* c, double* tflops);
+int tc05_selftest(Ctx* c, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);
 
 }  // namespace svdb200

@@ -16,6 +16,10 @@ namespace svdb200 {
 template <typename T> int rank_update_fast(Ctx*, T*, size_t, int, int, int, const T*, const T*, size_t);
 template <typename T> int gemm_tn_fast(Ctx*, const T*, const T*, size_t, int, int, int, T*, int, int);
 template <typename T> int gemm_nn_fast(Ctx*, const T*, size_t, int, int, int, const T*, T*, int, int);
+// tcgen05 / TMEM / TMA kernels for FP32 (gemm_tc05.cu): same convention
+template <typename T> int rank_update_tc05(Ctx*, T*, size_t, int, int, int, const T*, const T*, size_t);
+template <typename T> int gemm_tn_tc05(Ctx*, const T*, const T*, size_t, int, int, int, T*);
+template <typename T> int gemm_nn_tc05(Ctx*, const T*, size_t, int, int, int, const T*, T*);
 
 namespace {
 
@@ -286,6 +290,10 @@ int rank_update(Ctx* c, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b,
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     ProfScope ps(c, 3, 2.0 * (double)mrows * (double)ncols * (double)b);
     {
+        int st = rank_update_tc05<T>(c, cm, ldc, (int)mrows, (int)ncols, (int)b, p, q, ldq);
+        if (st != 1) return st;
+    }
+    {
         int st = rank_update_fast<T>(c, cm, ldc, (int)mrows, (int)ncols, (int)b, p, q, ldq);
         if (st != 1) return st;
     }
@@ -298,6 +306,10 @@ int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t nc
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
     ProfScope ps(c, 1, 2.0 * (double)mrows * (double)ncols * (double)b);
+    {
+        int st = gemm_tn_tc05<T>(c, v, cm, ldc, M, N, B, w);
+        if (st != 1) return st;
+    }
     if (B == 32 || B == 64) {          // pipelined kernel: 128-column tiles, 16-row stages
         long long tiles_f = (N + 127) / 128;
         int splits_f = pick_splits(tiles_f, (M + KC - 1) / KC, c->num_sms, c->wpart_elems, (size_t)B * N);
@@ -348,6 +360,10 @@ int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t 
     if (b == 0 || b > (size_t)kMaxBand) return SVDB200_E_CAPACITY;
     const int M = (int)mrows, N = (int)ncols, B = (int)b, KC = 32;
     ProfScope ps(c, 2, 2.0 * (double)mrows * (double)ncols * (double)b);
+    {
+        int st = gemm_nn_tc05<T>(c, cm, ldc, M, N, B, ut, w);
+        if (st != 1) return st;
+    }
     if (B == 32 || B == 64) {          // pipelined kernel: 128-row tiles, 32-column stages
         long long tiles_f = (M + 127) / 128;
         int splits_f = pick_splits(tiles_f, (N + KC - 1) / KC, c->num_sms, c->wpart_elems, (size_t)M * B);
