@@ -155,6 +155,61 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def north_star_shape(capi, torch, stream, dev, local_rank, dt, peaks, hbm_peak, nb=16384, bb=64):
+    """Stage 1 at BASELINE configs[2]'s shape: whole-stage device time, then a profiled pass (per-launch CUDA events)."""
+    try:
+        tdt = torch.float64 if dt == np.float64 else torch.float32
+        esz = 8 if dt == np.float64 else 4
+        hb = capi.Handle(nb, bb, dt, device=local_rank)
+        hb.set_stream(stream.cuda_stream)
+        ab = torch.empty(nb, nb, device=dev, dtype=tdt)
+        best = None
+        for rep in range(2):
+            hb.fill_uniform_dev(ab.data_ptr(), nb * nb, 586 + nb, 0.0, 5.0)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            hb.dense_to_band_dev(ab.data_ptr(), nb, bb)
+            b1.record(stream)
+            torch.cuda.synchronize()
+            t = b0.elapsed_time(b1)
+            best = t if best is None else min(best, t)
+        t_s1 = best
+        hb.fill_uniform_dev(ab.data_ptr(), nb * nb, 586 + nb, 0.0, 5.0)
+        torch.cuda.synchronize()
+        hb.reset_profile(); hb.set_profile(True)
+        hb.dense_to_band_dev(ab.data_ptr(), nb, bb)
+        torch.cuda.synchronize()
+        hb.set_profile(False)
+        pb = hb.get_profile()
+        gms = sum(pb[k]["ms"] for k in ("gemm_tn", "gemm_nn", "rank_update"))
+        gwork = sum(pb[k]["work"] for k in ("gemm_tn", "gemm_nn", "rank_update"))
+        tf = gwork / (gms * 1e-3) * 1e-12
+        # algorithmic HBM bytes of the update: C read once per GEMM, read + written once per rank-b update
+        gbytes = (pb["gemm_tn"]["work"] + pb["gemm_nn"]["work"] + 2 * pb["rank_update"]["work"]) / (2.0 * bb) * esz
+        out = {"n": nb, "band": bb, "dtype": "f64" if dt == np.float64 else "f32", "stage1_ms": round(t_s1, 2),
+               "stage1_tflops": round(flops(nb) / (t_s1 * 1e-3) * 1e-12, 2), "trailing_update_tflops": round(tf, 2),
+               "trailing_update_hbm_gbs": round(gbytes / (gms * 1e-3) * 1e-9, 1),
+               "trailing_update_frac_of_hbm_peak": round(gbytes / (gms * 1e-3) * 1e-9 / hbm_peak, 4)}
+        if dt == np.float64:
+            out["trailing_update_frac_of_fp64_dmma_peak"] = round(tf / peaks["dmma_f64_tflops"], 4)
+            out["tensor_path"] = "mma.sync.m8n8k4.f64 (DMMA); tcgen05.mma has no f64 kind"
+        else:
+            pk = peaks.get("tf32_tcgen05_tflops")
+            if pk:
+                out["trailing_update_frac_of_3xtf32_tcgen05_peak"] = round(tf / (pk / 3.0), 4)
+            out["tensor_path"] = "tcgen05.mma kind::tf32 x3 (hi/lo split), accumulator in TMEM, operands by TMA"
+        out["classes"] = {k: {"ms": round(x["ms"], 2), "launches": x["launches"],
+                              "tflops": round(x["work"] / (x["ms"] * 1e-3) * 1e-12, 2) if x["ms"] > 0 else None}
+                          for k, x in pb.items() if x["launches"]}
+        hb.close()
+        del ab
+        torch.cuda.empty_cache()
+        return out
+    except Exception as ex:   # a capacity problem must not take the bench line down
+        return {"error": str(ex)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,7 +337,7 @@ def main():
                            "stage1_gflops": round(flops(n) / (t1 * 1e-3) * 1e-9, 1)})
 
     # ---- roofline of the dominant kernel: profiled pass, CUDA events per launch ------------------
-    roofline, prof_out, peaks, big = None, None, {}, None
+    roofline, prof_out, peaks, big, big32 = None, None, {}, None, None
     if rank == 0:
         h = handles["f64"]
         peaks = {"dfma_tflops": h.probe_peak(0), "dmma_f64_tflops": h.probe_peak(1), "ffma_tflops": h.probe_peak(2),
@@ -329,40 +384,15 @@ def main():
                         "unit": "TFLOP/s", "frac": round(ach / peaks["dmma_f64_tflops"], 4), "traffic": None,
                         "peak_source": "FP64 DMMA mma.sync.m8n8k4 register-resident probe measured in this run",
                         "launches_timed": v["launches"], "avg_launch_us": round(v["ms"] / max(v["launches"], 1) * 1e3, 2)}
-        # stage-1 trailing update at the north-star shape (n = 16384, band 64, double), per-launch CUDA events
+        # stage-1 trailing update at the north-star shape (n = 16384, band 64), per-launch CUDA events:
+        # double on DMMA mma.sync (tcgen05 has no f64 kind), float on tcgen05/TMEM/TMA (3xTF32)
         if not args.sizes and not args.no_big:
             try:
-                nb, bb = 16384, 64
-                hb = capi.Handle(nb, bb, np.float64, device=local_rank)
-                hb.set_stream(stream.cuda_stream)
-                ab = torch.empty(nb, nb, device=dev, dtype=torch.float64)
-                hb.fill_uniform_dev(ab.data_ptr(), nb * nb, 586 + nb, 0.0, 5.0)
-                torch.cuda.synchronize()
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b0.record(stream)
-                hb.dense_to_band_dev(ab.data_ptr(), nb, bb)
-                b1.record(stream)
-                torch.cuda.synchronize()
-                t_s1 = b0.elapsed_time(b1)
-                hb.fill_uniform_dev(ab.data_ptr(), nb * nb, 586 + nb, 0.0, 5.0)
-                torch.cuda.synchronize()
-                hb.reset_profile(); hb.set_profile(True)
-                hb.dense_to_band_dev(ab.data_ptr(), nb, bb)
-                torch.cuda.synchronize()
-                hb.set_profile(False)
-                pb = hb.get_profile()
-                gms = sum(pb[k]["ms"] for k in ("gemm_tn", "gemm_nn", "rank_update"))
-                gwork = sum(pb[k]["work"] for k in ("gemm_tn", "gemm_nn", "rank_update"))
-                big = {"n": nb, "band": bb, "dtype": "f64", "stage1_ms": round(t_s1, 2), "stage1_tflops": round(flops(nb) / (t_s1 * 1e-3) * 1e-12, 2),
-                       "trailing_update_tflops": round(gwork / (gms * 1e-3) * 1e-12, 2),
-                       "trailing_update_frac_of_fp64_dmma_peak": round(gwork / (gms * 1e-3) * 1e-12 / peaks["dmma_f64_tflops"], 4),
-                       "classes": {k: {"ms": round(x["ms"], 2), "launches": x["launches"],
-                                       "tflops": round(x["work"] / (x["ms"] * 1e-3) * 1e-12, 2) if x["ms"] > 0 else None}
-                                   for k, x in pb.items() if x["launches"]}}
-                hb.close()
-                del ab
-            except Exception as ex:   # a capacity problem must not take the bench line down
-                big = {"error": str(ex)}
+                peaks["tf32_tcgen05_tflops"] = handles["f32"].probe_peak(4)
+            except Exception:
+                pass
+            big = north_star_shape(capi, torch, stream, dev, local_rank, np.float64, peaks, hbm_peak or 6650.0)
+            big32 = north_star_shape(capi, torch, stream, dev, local_rank, np.float32, peaks, hbm_peak or 6650.0)
     # ---- e2e: host-pointer C-ABI call with pinned host buffers --------------------------------------
     from svdsolver_b200.synth import uniform_matrix
     e2e = None
@@ -449,7 +479,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_classes_f64": prof_out, "north_star_shape": big, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
+            "kernel_classes_f64": prof_out, "north_star_shape": big, "north_star_shape_f32": big32, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
         }
         print(json.dumps(line), flush=True)
     for h in handles.values():

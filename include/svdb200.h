@@ -149,6 +149,11 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops);
  * the updated block has at least min_elems elements (default), 2: always (tests).  min_elems <= 0
  * keeps the current threshold.  No effect on FP64 handles (tcgen05.mma has no f64 kind). */
 int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
+/* Singular values of the bidiagonal (svdb200_bidiag_qr_*, svdb200_svdvals_*): method 0 = automatic (the
+ * reference's zero-shift QR sweeps, serial::qrd svd_serial.h:368, for n <= auto_limit, bisection on the
+ * Golub-Kahan form above: zero-shift QR needs ~n log(1/tol) sweeps), 1 = always zero-shift QR, 2 = always
+ * bisection.  auto_limit == 0 keeps the current limit (default 1024). */
+int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit);
 /* Unit test of the tcgen05 building blocks (TMA box -> swizzled shared memory -> UMMA descriptors -> TMEM ->
  * tcgen05.ld): D(128 x 64) = A(128 x 32) B(32 x 64) in one TF32 pass.  a_mn/b_mn select the operand storage:
  * 0 = K-major (a: 128 x 32 row-major, b: B^T 64 x 32 row-major), 1 = MN-major (a: A^T 32 x 128, b: B 32 x 64).

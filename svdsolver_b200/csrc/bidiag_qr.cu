@@ -164,6 +164,9 @@ int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma) {
     if (n < 2) return SVDB200_E_SHAPE;
     if (n > c->max_n) return SVDB200_E_CAPACITY;
     ProfScope ps(c, 5, (double)n);
+    // zero-shift QR needs ~n log(1/tol) sweeps: beyond a moderate n the independent-per-value bisection
+    // solver (bidiag_bisect.cu) takes over
+    if (c->qr_method == 2 || (c->qr_method == 0 && n > c->qr_auto_limit)) return bidiag_bisect<T>(c, d, e, n, sigma);
     int npad = 1;
     while ((size_t)npad < n) npad <<= 1;
     // sort buffer: reuse the stage-2 progress array region is int-sized; use wpart (>= 2*max_n elems)

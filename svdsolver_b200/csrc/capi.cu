@@ -407,7 +407,7 @@ int svdb200_destroy(svdb200_handle h) {
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
-                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit};
+                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);
@@ -610,6 +610,15 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
     SVDB_CHECK(c, cudaSetDevice(c->device));
     if (kind == 4) return probe_tc05_tf32(c, tflops);
     return probe_peak(c, kind, tflops);
+}
+
+int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit) {
+    if (!h || method < 0 || method > 2) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->qr_method = method;
+    if (auto_limit > 0) c->qr_auto_limit = auto_limit;
+    for (auto* s : c->pool) if (s) { s->qr_method = method; if (auto_limit > 0) s->qr_auto_limit = auto_limit; }
+    return 0;
 }
 
 int svdb200_tc05_selftest(svdb200_handle h, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump) {

@@ -61,7 +61,11 @@ struct Ctx {
     void* tcsplit = nullptr;
     size_t tcsplit_elems = 0;
     int use_tc05 = 1;                       // 0 off, 1 when the update is large enough, 2 always (tests)
-    long long tc05_min_elems = 1LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
+    long long tc05_min_elems = 8LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
+    // singular values of the bidiagonal: 0 auto (zero-shift QR up to qr_auto_limit, bisection above), 1 QR, 2 bisection
+    int qr_method = 0;
+    size_t qr_auto_limit = 1024;
+    void* bis_ws = nullptr;                 // bisection workspace: params + 2 * max_n squared off-diagonals (double)
 };
 
 // Brackets one kernel launch with events when profiling is on (serialises host and device; the
@@ -168,6 +172,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsi
 // ---- internal entry points (one per .cu) ----------------------------------------------------------
 template <typename T> int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e);
 template <typename T> int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma);
+template <typename T> int bidiag_bisect(Ctx* c, const T* d, const T* e, size_t n, T* sigma);
 template <typename T> int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band);
 template <typename T> int stage1_tile_order(Ctx* c, T* a, size_t n, size_t band);
 template <typename T> int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, T* w);

@@ -309,3 +309,33 @@ def test_batched_svdvals(capi, suf, count, n, b):
             s1, _ = h.svdvals(a[i], b)
             assert np.array_equal(sig[i], s1)
     assert np.all(np.diff(sig, axis=1) <= 0)
+
+
+# ------------------------------------------------------------------ bisection solver ------------------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n", [2, 3, 100, 1000, 5000])
+def test_bidiag_bisection_vs_lapack(capi, suf, n):
+    """svdb200_set_qr_method(2): bisection on the Golub-Kahan form, sigma vs LAPACK on the same bidiagonal."""
+    rng = np.random.default_rng(n)
+    d = (rng.random(n) * 5).astype(DT[suf])
+    e = (rng.random(n - 1) * 5 - 2.5).astype(DT[suf])
+    ref = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+    with handle(capi, n, 1, suf) as h:
+        h.set_qr_method(2)
+        sigma, sweeps = h.bidiag_qr(d, e)
+    assert np.all(np.diff(sigma) <= 0)
+    tol = 2e-7 if suf == "f32" else (1e-14 if n < 1000 else 5e-14)    # LAPACK's own methods differ by 3e-14 at n = 5000
+    assert np.abs(sigma.astype(np.float64) - ref).max() <= tol * ref[0]
+
+
+def test_bidiag_auto_method_switches_to_bisection(capi):
+    """above the auto limit the QR entry point must not need zero-shift sweeps (sweeps == 0) and stays accurate"""
+    n = 3000
+    rng = np.random.default_rng(7)
+    d = rng.random(n) * 5
+    e = rng.random(n - 1) * 5
+    ref = np.linalg.svd(np.diag(d) + np.diag(e, 1), compute_uv=False)
+    with handle(capi, n, 1, "f64") as h:
+        sigma, sweeps = h.bidiag_qr(d, e)
+    assert sweeps == 0
+    assert np.abs(sigma - ref).max() <= 1e-14 * ref[0]
