@@ -183,9 +183,71 @@ int probe_peak(Ctx* c, int kind, double* tflops) {
 // Shards by matrix across GPUs at the caller's level (one handle per GPU), no collective.
 constexpr int kBatchPool = 16;
 
+// Small matrices (n <= 1024, band <= 64): every kernel of the path runs ONCE PER STEP FOR THE WHOLE BATCH -- a
+// thread-block cluster per matrix for the panels (panel resident in cluster shared memory), one grid slice per
+// matrix for the three update GEMMs, groups of CTAs that pipeline the sweeps of one matrix each for stage 2, one
+// thread per singular value for the bisection -- instead of ~80 launches per matrix.  The matrices of a chunk stay
+// L2 / HBM resident; workspace is (5 n b + 2 n) elements per matrix of the chunk.
+template <typename T>
+int batched_small(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
+    const int b = (int)band;
+    const size_t per_mat = 5 * n * band + 2 * n;
+    size_t chunk = std::min<size_t>(count, 8192);
+    while (chunk > 1 && chunk * per_mat * sizeof(T) > ((size_t)2 << 30)) chunk = (chunk + 1) / 2;
+    const size_t need = chunk * per_mat * sizeof(T);
+    if (c->batch_ws_bytes < need) {
+        if (c->batch_ws) cudaFree(c->batch_ws);
+        c->batch_ws = nullptr; c->batch_ws_bytes = 0;
+        SVDB_CHECK(c, cudaMalloc(&c->batch_ws, need));
+        c->batch_ws_bytes = need;
+    }
+    const size_t sV = n * band, sA = n * n;
+    T* Vq = reinterpret_cast<T*>(c->batch_ws);
+    T* V2q = Vq + chunk * sV;
+    T* Vl = V2q + chunk * sV;
+    T* V2l = Vl + chunk * sV;
+    T* W = V2l + chunk * sV;
+    T* dall = W + chunk * sV;
+    T* eall = dall + chunk * n;
+    for (size_t z0 = 0; z0 < count; z0 += chunk) {
+        const int cnt = (int)std::min(chunk, count - z0);
+        T* a0 = a + z0 * sA;
+        for (size_t k = 0; k < n; k += band) {           // same panel sequence as stage1_panel_order (svd_cpu.h:382-423)
+            const int m = (int)(n - k), nc = (int)(n - k - band);
+            const bool has_lq = (k + band < n - 1);
+            SVDB_TRY((panel_batched<T, false>(c, a0 + k * n + k, n, sA, m, b, Vq, V2q, sV, cnt)));
+            if (nc > 0) {
+                T* A2 = a0 + k * n + k + band;
+                SVDB_TRY(gemm_tn_batched<T>(c, Vq, sV, A2, n, sA, m, nc, b, W, sV, cnt));                     // W = V^T A2
+                SVDB_TRY(rank_update_batched<T>(c, A2, n, sA, m, nc, b, V2q, sV, W, (size_t)nc, sV, cnt));     // A2 += (V S^T) W
+                if (has_lq) {
+                    SVDB_TRY((panel_batched<T, true>(c, A2, n, sA, nc, b, Vl, V2l, sV, cnt)));                // LQ of the row panel
+                    const int mr = m - b;
+                    if (mr > 0) {
+                        T* A3 = a0 + (k + band) * n + k + band;
+                        SVDB_TRY(gemm_nn_batched<T>(c, A3, n, sA, mr, nc, b, Vl, sV, W, sV, cnt));             // W = A3 U^T
+                        SVDB_TRY(rank_update_batched<T>(c, A3, n, sA, mr, nc, b, W, sV, V2l, (size_t)nc, sV, cnt));
+                    }
+                }
+            }
+        }
+        SVDB_TRY(stage2_chase_batched<T>(c, a0, n, band, dall, eall, cnt));
+        if (c->qr_method == 1) {                          // the reference's zero-shift QR sweeps, one CTA per matrix
+            for (int i = 0; i < cnt; ++i) SVDB_TRY(bidiag_qr<T>(c, dall + (size_t)i * n, eall + (size_t)i * n, n, sigma + (z0 + i) * n));
+        } else {
+            for (int i0 = 0; i0 < cnt; i0 += 32768) {
+                const int ic = std::min(32768, cnt - i0);
+                SVDB_TRY(bidiag_bisect_batched<T>(c, dall + (size_t)i0 * n, eall + (size_t)i0 * n, n, sigma + (z0 + i0) * n, ic));
+            }
+        }
+    }
+    return 0;
+}
+
 template <typename T>
 int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
     if (count == 0) return 0;
+    if (n <= 1024 && band <= 64 && c->cluster_ok >= 8 && n >= 2) return batched_small<T>(c, a, count, n, band, sigma);
     if (c->pool_n != n || c->pool_band != band) {
         for (auto& h : c->pool) if (h) { svdb200_destroy(reinterpret_cast<svdb200_handle>(h)); h = nullptr; }
         c->pool.clear();
@@ -407,7 +469,7 @@ int svdb200_destroy(svdb200_handle h) {
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
-                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws};
+                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);

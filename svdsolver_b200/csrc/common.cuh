@@ -65,7 +65,13 @@ struct Ctx {
     // singular values of the bidiagonal: 0 auto (zero-shift QR up to qr_auto_limit, bisection above), 1 QR, 2 bisection
     int qr_method = 0;
     size_t qr_auto_limit = 1024;
-    void* bis_ws = nullptr;                 // bisection workspace: params + 2 * max_n squared off-diagonals (double)
+    void* bis_ws = nullptr;
+    size_t bis_ws_elems = 0;
+    // batched small-matrix driver: per-matrix progress counters, reflector / W workspaces, d / e rows
+    int* batch_prog = nullptr;
+    size_t batch_prog_elems = 0;
+    void* batch_ws = nullptr;
+    size_t batch_ws_bytes = 0;                 // bisection workspace: params + 2 * max_n squared off-diagonals (double)
 };
 
 // Brackets one kernel launch with events when profiling is on (serialises host and device; the
@@ -178,6 +184,13 @@ template <typename T> int stage1_tile_order(Ctx* c, T* a, size_t n, size_t band)
 template <typename T> int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, T* w);
 template <typename T> int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* ut, T* w);
 template <typename T> int rank_update(Ctx* c, T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, const T* p, const T* q, size_t ldq);
+// batched (uniform-shape) building blocks: element strides sX between consecutive matrices
+template <typename T> int rank_update_batched(Ctx* c, T* cm, size_t ldc, size_t sC, int M, int N, int K, const T* p, size_t sP, const T* q, size_t ldq, size_t sQ, int count);
+template <typename T> int gemm_tn_batched(Ctx* c, const T* v, size_t sV, const T* cm, size_t ldc, size_t sC, int M, int N, int B, T* w, size_t sW, int count);
+template <typename T> int gemm_nn_batched(Ctx* c, const T* cm, size_t ldc, size_t sC, int M, int N, int B, const T* ut, size_t sU, T* w, size_t sW, int count);
+template <typename T, bool kTrans> int panel_batched(Ctx* c, T* a, size_t lda, size_t sA, int m, int b, T* V, T* V2, size_t sV, int count);
+template <typename T> int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int count);
+template <typename T> int bidiag_bisect_batched(Ctx* c, const T* d, const T* e, size_t n, T* sigma, int count);
 template <typename T> int fill_uniform(Ctx* c, T* a, size_t count, unsigned long long seed, double lo, double hi);
 template <typename T> int mse_metric(Ctx* c, const T* a, const T* b, size_t n, size_t band, T* out_host);
 template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma);

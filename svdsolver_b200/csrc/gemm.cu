@@ -8,6 +8,7 @@
 // FP64 runs on the tensor cores through mma.sync.m8n8k4.f64 (DMMA): tcgen05.mma has no f64 kind
 // (SURVEY 0.6).  FP32 runs as 3xTF32 error-compensated mma.sync.m16n8k8 (hi*hi + hi*lo + lo*hi,
 // fp32 accumulate), which keeps ~fp32 accuracy through the n/b chained updates.
+#include <algorithm>
 #include "common.cuh"
 
 namespace svdb200 {
@@ -144,9 +145,10 @@ __device__ __forceinline__ void load_tile(T* __restrict__ dst, int lds, const T*
 template <typename T, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32)
 rank_update_kernel(T* __restrict__ C, size_t ldc, int M, int N, int K, const T* __restrict__ P, const T* __restrict__ Q,
-                   size_t ldq) {
+                   size_t ldq, size_t sC, size_t sP, size_t sQ) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int BM = WM * 32, BN = WN * 16;
+    C += (size_t)blockIdx.z * sC; P += (size_t)blockIdx.z * sP; Q += (size_t)blockIdx.z * sQ;   // batched: one matrix per z
     const int kp = ((K + WarpMma<T>::kStep - 1) / WarpMma<T>::kStep) * WarpMma<T>::kStep;
     const int lda = pad_kcontig<T>(kp), ldb = pad_mncontig<T>(BN);
     T* Ps = reinterpret_cast<T*>(smem_raw);
@@ -180,13 +182,19 @@ rank_update_kernel(T* __restrict__ C, size_t ldc, int M, int N, int K, const T* 
 template <typename T, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_tn_kernel(const T* __restrict__ V, const T* __restrict__ C, size_t ldc, int M, int N, int B, T* __restrict__ Wpart,
-               int rows_per_split) {
+               int rows_per_split, int nsplit, size_t sV, size_t sC, size_t sW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int BMT = WM * 32, BN = WN * 16, KC = 32;
     const int lda = pad_mncontig<T>(BMT), ldb = pad_mncontig<T>(BN);
     T* Vs = reinterpret_cast<T*>(smem_raw);
     T* Cs = Vs + KC * lda;
-    const int n0 = blockIdx.x * BN, split = blockIdx.y, i0 = blockIdx.z * BMT;
+    int split = blockIdx.y;
+    if (nsplit > 0) {                                     // batched: blockIdx.y = matrix * nsplit + split
+        const int bat = blockIdx.y / nsplit;
+        split = blockIdx.y - bat * nsplit;
+        V += (size_t)bat * sV; C += (size_t)bat * sC; Wpart += (size_t)bat * sW;
+    }
+    const int n0 = blockIdx.x * BN, i0 = blockIdx.z * BMT;
     const int r_begin = split * rows_per_split;
     const int r_end = min(M, r_begin + rows_per_split);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,13 +223,19 @@ gemm_tn_kernel(const T* __restrict__ V, const T* __restrict__ C, size_t ldc, int
 template <typename T, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_nn_kernel(const T* __restrict__ C, size_t ldc, int M, int N, int B, const T* __restrict__ Ut, T* __restrict__ Wpart,
-               int cols_per_split) {
+               int cols_per_split, int nsplit, size_t sC, size_t sU, size_t sW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int BM = WM * 32, BNB = WN * 16, KC = 32;
     const int lda = pad_kcontig<T>(KC), ldb = pad_mncontig<T>(BNB);
     T* Cs = reinterpret_cast<T*>(smem_raw);
     T* Us = Cs + BM * lda;
-    const int m0 = blockIdx.x * BM, split = blockIdx.y, j0 = blockIdx.z * BNB;
+    int split = blockIdx.y;
+    if (nsplit > 0) {                                     // batched: blockIdx.y = matrix * nsplit + split
+        const int bat = blockIdx.y / nsplit;
+        split = blockIdx.y - bat * nsplit;
+        C += (size_t)bat * sC; Ut += (size_t)bat * sU; Wpart += (size_t)bat * sW;
+    }
+    const int m0 = blockIdx.x * BM, j0 = blockIdx.z * BNB;
     const int c_begin = split * cols_per_split;
     const int c_end = min(N, c_begin + cols_per_split);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,7 +278,7 @@ int launch_rank_update(Ctx* c, T* cm, size_t ldc, int M, int N, int K, const T* 
     auto kern = rank_update_kernel<T, WM, WN>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    kern<<<grid, WM * WN * 32, smem, c->stream>>>(cm, ldc, M, N, K, p, q, ldq);
+    kern<<<grid, WM * WN * 32, smem, c->stream>>>(cm, ldc, M, N, K, p, q, ldq, (size_t)0, (size_t)0, (size_t)0);
     SVDB_CHECK(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -339,7 +353,7 @@ int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t nc
     {                                                                                                         \
         auto kern = gemm_tn_kernel<T, WMv, WNv>;                                                              \
         SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, 256, smem, c->stream>>>(v, cm, ldc, M, N, B, out, rows_per_split);                       \
+        kern<<<grid, 256, smem, c->stream>>>(v, cm, ldc, M, N, B, out, rows_per_split, 0, (size_t)0, (size_t)0, (size_t)0);                       \
     }
     if (wm == 1) SVDB_LAUNCH_TN(1, 8) else if (wm == 2) SVDB_LAUNCH_TN(2, 4) else SVDB_LAUNCH_TN(4, 2)
 #undef SVDB_LAUNCH_TN
@@ -393,7 +407,7 @@ int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t 
     {                                                                                                         \
         auto kern = gemm_nn_kernel<T, WMv, WNv>;                                                              \
         SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, 256, smem, c->stream>>>(cm, ldc, M, N, B, ut, out, cols_per_split);                      \
+        kern<<<grid, 256, smem, c->stream>>>(cm, ldc, M, N, B, ut, out, cols_per_split, 0, (size_t)0, (size_t)0, (size_t)0);                      \
     }
     if (wm == 8) SVDB_LAUNCH_NN(8, 1) else if (wm == 4) SVDB_LAUNCH_NN(4, 2) else if (wm == 2) SVDB_LAUNCH_NN(2, 4) else SVDB_LAUNCH_NN(1, 8)
 #undef SVDB_LAUNCH_NN
@@ -407,6 +421,83 @@ int gemm_nn(Ctx* c, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t 
     }
     return 0;
 }
+
+// ---- batched variants (uniform shapes, one matrix per grid slice): the small-matrix driver of capi.cu ----------------
+template <typename T>
+int rank_update_batched(Ctx* c, T* cm, size_t ldc, size_t sC, int M, int N, int K, const T* p, size_t sP, const T* q, size_t ldq,
+                        size_t sQ, int count) {
+    if (M <= 0 || N <= 0 || count <= 0) return 0;
+    if (K <= 0 || K > kMaxBand) return SVDB200_E_CAPACITY;
+    constexpr int WM = 4, WN = 4, BM = WM * 32, BN = WN * 16;
+    const int kp = ((K + WarpMma<T>::kStep - 1) / WarpMma<T>::kStep) * WarpMma<T>::kStep;
+    size_t smem = ((size_t)BM * pad_kcontig<T>(kp) + (size_t)kp * pad_mncontig<T>(BN)) * sizeof(T);
+    auto kern = rank_update_kernel<T, WM, WN>;
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int z0 = 0; z0 < count; z0 += 32768) {
+        const int zc = std::min(32768, count - z0);
+        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, zc);
+        kern<<<grid, WM * WN * 32, smem, c->stream>>>(cm + (size_t)z0 * sC, ldc, M, N, K, p + (size_t)z0 * sP, q + (size_t)z0 * sQ, ldq, sC, sP, sQ);
+        SVDB_CHECK(c, cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+template <typename T>
+int gemm_tn_batched(Ctx* c, const T* v, size_t sV, const T* cm, size_t ldc, size_t sC, int M, int N, int B, T* w, size_t sW, int count) {
+    if (M <= 0 || N <= 0 || count <= 0) return 0;
+    if (B <= 0 || B > 64) return SVDB200_E_CAPACITY;
+    constexpr int KC = 32;
+    for (int z0 = 0; z0 < count; z0 += 32768) {
+        const int zc = std::min(32768, count - z0);
+#define SVDB_LAUNCH_TNB(WMv, WNv)                                                                              \
+    {                                                                                                          \
+        constexpr int BMT = WMv * 32, BN = WNv * 16;                                                           \
+        size_t smem = ((size_t)KC * pad_mncontig<T>(BMT) + (size_t)KC * pad_mncontig<T>(BN)) * sizeof(T);     \
+        auto kern = gemm_tn_kernel<T, WMv, WNv>;                                                               \
+        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        dim3 grid((N + BN - 1) / BN, zc, (B + BMT - 1) / BMT);                                                 \
+        kern<<<grid, 256, smem, c->stream>>>(v + (size_t)z0 * sV, cm + (size_t)z0 * sC, ldc, M, N, B, w + (size_t)z0 * sW, M, 1, sV, sC, sW); \
+    }
+        if (B <= 32) SVDB_LAUNCH_TNB(1, 8) else SVDB_LAUNCH_TNB(2, 4)
+#undef SVDB_LAUNCH_TNB
+        SVDB_CHECK(c, cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+template <typename T>
+int gemm_nn_batched(Ctx* c, const T* cm, size_t ldc, size_t sC, int M, int N, int B, const T* ut, size_t sU, T* w, size_t sW, int count) {
+    if (M <= 0 || N <= 0 || count <= 0) return 0;
+    if (B <= 0 || B > 64) return SVDB200_E_CAPACITY;
+    constexpr int KC = 32;
+    for (int z0 = 0; z0 < count; z0 += 32768) {
+        const int zc = std::min(32768, count - z0);
+#define SVDB_LAUNCH_NNB(WMv, WNv)                                                                              \
+    {                                                                                                          \
+        constexpr int BM = WMv * 32, BNB = WNv * 16;                                                           \
+        size_t smem = ((size_t)BM * pad_kcontig<T>(KC) + (size_t)KC * pad_mncontig<T>(BNB)) * sizeof(T);      \
+        auto kern = gemm_nn_kernel<T, WMv, WNv>;                                                               \
+        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        dim3 grid((M + BM - 1) / BM, zc, (B + BNB - 1) / BNB);                                                 \
+        kern<<<grid, 256, smem, c->stream>>>(cm + (size_t)z0 * sC, ldc, M, N, B, ut + (size_t)z0 * sU, w + (size_t)z0 * sW, N, 1, sC, sU, sW); \
+    }
+        if (B <= 16) SVDB_LAUNCH_NNB(8, 1) else if (B <= 32) SVDB_LAUNCH_NNB(4, 2) else SVDB_LAUNCH_NNB(2, 4)
+#undef SVDB_LAUNCH_NNB
+        SVDB_CHECK(c, cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+#define SVDB_INST_BATCHED(T)                                                                                                        \
+    template int rank_update_batched<T>(Ctx*, T*, size_t, size_t, int, int, int, const T*, size_t, const T*, size_t, size_t, int); \
+    template int gemm_tn_batched<T>(Ctx*, const T*, size_t, const T*, size_t, size_t, int, int, int, T*, size_t, int);             \
+    template int gemm_nn_batched<T>(Ctx*, const T*, size_t, size_t, int, int, int, const T*, size_t, T*, size_t, int);
+SVDB_INST_BATCHED(float)
+SVDB_INST_BATCHED(double)
+#undef SVDB_INST_BATCHED
 
 template int rank_update<float>(Ctx*, float*, size_t, size_t, size_t, size_t, const float*, const float*, size_t);
 template int rank_update<double>(Ctx*, double*, size_t, size_t, size_t, size_t, const double*, const double*, size_t);

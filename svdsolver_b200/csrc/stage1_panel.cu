@@ -21,6 +21,7 @@
 //   * partial sums are combined in a fixed association, so the result is deterministic.
 // Outputs: R (or L) written into A with exact zeros below the diagonal of the panel, V (m x b,
 // unit diagonal explicit), V2 = V S^T, and S.
+#include <algorithm>
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -41,10 +42,15 @@ constexpr int kPanelThreads = 256;
 template <typename T, bool kTrans, bool kCluster>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_cta, T* __restrict__ V, T* __restrict__ V2,
-                    T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar) {
+                    T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar, int Gb, size_t sA, size_t sV) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int G = gridDim.x, g = blockIdx.x;
+    // Gb > 0: batched launch, clusters of Gb CTAs, one matrix (element strides sA / sV) per cluster
+    const int G = Gb > 0 ? Gb : gridDim.x, g = Gb > 0 ? blockIdx.x % Gb : blockIdx.x;
+    if (Gb > 0) {
+        const size_t mat = blockIdx.x / Gb;
+        A += mat * sA; V += mat * sV; V2 += mat * sV;
+    }
     const int r0 = g * rows_per_cta;
     const int R = max(0, min(rows_per_cta, m - r0));     // local rows
     const int ld = b + 1;
@@ -275,7 +281,7 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, rows, V, V2, S, red, bar);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, rows, V, V2, S, red, bar, 0, (size_t)0, (size_t)0);
             if (e == cudaSuccess) {
                 c->launches++;
                 return 0;
@@ -297,7 +303,9 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
     auto kern = panel_factor_kernel<T, kTrans, false>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), stream));
-    void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar};
+    int gb0 = 0;
+    size_t zero = 0;
+    void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar, &gb0, &zero, &zero};
     SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, stream));
     c->launches++;
     return 0;
@@ -312,6 +320,49 @@ template int launch_panel_public<float, false>(Ctx*, float*, size_t, int, int);
 template int launch_panel_public<float, true>(Ctx*, float*, size_t, int, int);
 template int launch_panel_public<double, false>(Ctx*, double*, size_t, int, int);
 template int launch_panel_public<double, true>(Ctx*, double*, size_t, int, int);
+
+// Batched panels (uniform shape): one thread-block cluster per matrix, panel resident in the cluster's shared
+// memory, all-reduce over DSMEM.  Used by the small-matrix batched driver (BASELINE configs[4]).
+template <typename T, bool kTrans>
+int panel_batched(Ctx* c, T* a, size_t lda, size_t sA, int m, int b, T* V, T* V2, size_t sV, int count) {
+    if (count <= 0 || m <= 0) return 0;
+    int G = (m + 127) / 128;                       // <= 128 rows per CTA: few, fat CTAs (many matrices share the GPU)
+    if (G > 8) G = 8;
+    int rows = (m + G - 1) / G;
+    G = (m + rows - 1) / rows;
+    const size_t smem = panel_smem_bytes(rows, b, sizeof(T));
+    if (smem > 200 * 1024) return SVDB200_E_CAPACITY;
+    auto kern = panel_factor_kernel<T, kTrans, true>;
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    T* S = nullptr;
+    T* red = nullptr;
+    unsigned* bar = nullptr;
+    for (int z0 = 0; z0 < count; z0 += 16384) {
+        const int zc = std::min(16384, count - z0);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(G * zc));
+        cfg.blockDim = dim3(kPanelThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = G;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        T* az = a + (size_t)z0 * sA;
+        T* vz = V + (size_t)z0 * sV;
+        T* v2z = V2 + (size_t)z0 * sV;
+        SVDB_CHECK(c, cudaLaunchKernelEx(&cfg, kern, az, lda, m, b, rows, vz, v2z, S, red, bar, G, sA, sV));
+        c->launches++;
+    }
+    return 0;
+}
+template int panel_batched<float, false>(Ctx*, float*, size_t, size_t, int, int, float*, float*, size_t, int);
+template int panel_batched<float, true>(Ctx*, float*, size_t, size_t, int, int, float*, float*, size_t, int);
+template int panel_batched<double, false>(Ctx*, double*, size_t, size_t, int, int, double*, double*, size_t, int);
+template int panel_batched<double, true>(Ctx*, double*, size_t, size_t, int, int, double*, double*, size_t, int);
 
 // Driver: same panel sequence as svd_cpu.h:382-423 / svd_cuda_2.cu:1148-1213.
 //

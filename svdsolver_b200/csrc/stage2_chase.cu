@@ -16,6 +16,7 @@
 //     with k-ascending sums from 0, separate (never fused) multiply and add, reflector scalars in
 //     double -- so the kernel reproduces data/bidiagonal_* exactly when fed data/band_* (SURVEY 0.7);
 //   * the reference's window schedule is reproduced including its boundary behaviour.
+#include <algorithm>
 #include <climits>
 #include "common.cuh"
 
@@ -142,8 +143,9 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
     }
 }
 
-template <typename T, int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads, 1) stage2_chase_kernel(T* __restrict__ A, int n, int band, int* __restrict__ prog) {
+template <typename T, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T* __restrict__ A0, int n, int band, int* __restrict__ prog0,
+                                                                      int count, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = band, w = band + 1;
     const int ldr = c + 1, ldl = 2 * c + 1, ldh = c + 1;
@@ -155,7 +157,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) stage2_chase_kernel(T* __restr
     const size_t N = (size_t)n;
     const int tx = tid % c, ty = tid / c, tys = nt / c;   // 2-D view of the CTA: c columns x tys rows (nt >= c)
 
-    for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
+    // Batched use: the grid is split into groups of G CTAs; a group pipelines the sweeps of one matrix at a time
+    // (matrices group, group + #groups, ...).  Progress counters are per matrix and pre-zeroed, so a CTA that runs
+    // ahead into its group's next matrix only ever waits on counters of that matrix.  Single matrix: count = 1,
+    // G = gridDim.x.
+    const int grp = blockIdx.x / G, rank = blockIdx.x - grp * G, ngroups = gridDim.x / G;
+    for (int mat = grp; mat < count; mat += ngroups) {
+    T* __restrict__ A = A0 + (size_t)mat * N * N;
+    int* __restrict__ prog = prog0 + (size_t)mat * N;
+    for (int i = rank; i < n - 1; i += G) {
         const int top_j2 = min(i + 2 * w - 1, n);
         const int npairs = 1 + (n - top_j2) / c + 1;
         int fr = 0;                               // rows of the forwarded block sitting in WR (0: none)
@@ -245,11 +255,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) stage2_chase_kernel(T* __restr
         }
         if (tid == 0) st_release(&prog[i], INT_MAX);
     }
+    }
 }
 
 template <typename T>
 __global__ void extract_bidiagonal_kernel(const T* __restrict__ A, int n, T* __restrict__ d, T* __restrict__ e) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    A += (size_t)blockIdx.y * n * n;                 // batched: one matrix per blockIdx.y, d/e rows of length n
+    if (d) d += (size_t)blockIdx.y * n;
+    if (e) e += (size_t)blockIdx.y * n;
     if (i < n) {
         if (d) d[i] = A[(size_t)i * n + i];
         if (e && i + 1 < n) e[i] = A[(size_t)i * n + i + 1];
@@ -259,42 +273,62 @@ __global__ void extract_bidiagonal_kernel(const T* __restrict__ A, int n, T* __r
 }  // namespace
 
 template <typename T>
-int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) {
-    if (n < 2 || band < 1) return SVDB200_E_SHAPE;
+int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int count) {
+    if (n < 2 || band < 1 || count < 1) return SVDB200_E_SHAPE;
     if (n > (size_t)INT_MAX / 4) return SVDB200_E_CAPACITY;
     const int cb = (int)band;
-    ProfScope ps(c, 4, 4.0 * (double)band * (double)n * (double)n * sizeof(T));
+    ProfScope ps(c, 4, 4.0 * (double)band * (double)n * (double)n * sizeof(T) * count);
     size_t smem = (size_t)(2 * cb * (cb + 1) + cb * (2 * cb + 1) + cb * (cb + 1) + 8) * sizeof(T);
     int nt = stage2_threads(cb);
     if (nt > 1024) return SVDB200_E_CAPACITY;      // band <= 64
     if (cb * cb > kNewPerThread * nt) return SVDB200_E_CAPACITY;
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
-    // small bands run with <= 256 threads: instantiate that case without the 64-register cap
-    auto kern = nt <= 256 ? stage2_chase_kernel<T, 256> : stage2_chase_kernel<T, 1024>;
+    // small bands run with <= 256 threads: instantiate that case without the 64-register cap; a batch wants
+    // several CTAs per SM instead (the window product is FP64-issue bound for ~40 % of an op, the rest is latency)
+    auto kern = nt <= 256 ? (count > 1 ? stage2_chase_kernel<T, 256, 3> : stage2_chase_kernel<T, 256, 1>)
+                          : stage2_chase_kernel<T, 1024, 1>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVDB_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) return SVDB200_E_CAPACITY;
-    // No more sweeps can be in flight than the pipeline admits (one every 2 pairs).
+    // No more sweeps of one matrix can be in flight than the pipeline admits (one every 2 pairs).
     long long inflight = (long long)(n / band) / 2 + 2;
-    long long grid = (long long)per_sm * c->num_sms;
-    if (grid > inflight) grid = inflight;
-    if (grid > (long long)n - 1) grid = (long long)n - 1;
-    if (grid < 1) grid = 1;
-    SVDB_CHECK(c, cudaMemsetAsync(c->prog, 0, sizeof(int) * n, c->stream));
-    int ni = (int)n, bi = cb;
+    if (count > 1) inflight = std::max<long long>(1, (long long)(n / band + 1) / 2);   // no idle CTAs in a batch
+    long long slots = (long long)per_sm * c->num_sms;
+    long long G = std::min(inflight, std::min(slots, (long long)n - 1));
+    if (G < 1) G = 1;
+    long long groups = std::min((long long)count, slots / G);
+    if (groups < 1) groups = 1;
+    const long long grid = groups * G;
     int* prog = c->prog;
-    void* args[] = {&a, &ni, &bi, &prog};
+    if (count > 1) {
+        const size_t need = (size_t)count * n;
+        if (c->batch_prog_elems < need) {
+            if (c->batch_prog) cudaFree(c->batch_prog);
+            c->batch_prog = nullptr; c->batch_prog_elems = 0;
+            SVDB_CHECK(c, cudaMalloc(&c->batch_prog, sizeof(int) * need));
+            c->batch_prog_elems = need;
+        }
+        prog = c->batch_prog;
+    }
+    SVDB_CHECK(c, cudaMemsetAsync(prog, 0, sizeof(int) * n * (size_t)count, c->stream));
+    int ni = (int)n, bi = cb, cnt = count, gi = (int)G;
+    void* args[] = {&a, &ni, &bi, &prog, &cnt, &gi};
     SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(nt), args, smem, c->stream));
     c->launches++;
     if (d || e) {
-        extract_bidiagonal_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a, ni, d, e);
+        extract_bidiagonal_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)count), 256, 0, c->stream>>>(a, ni, d, e);
         SVDB_CHECK(c, cudaGetLastError());
         c->launches++;
     }
     return 0;
 }
 
+template <typename T>
+int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) { return stage2_chase_batched<T>(c, a, n, band, d, e, 1); }
+
+template int stage2_chase_batched<float>(Ctx*, float*, size_t, size_t, float*, float*, int);
+template int stage2_chase_batched<double>(Ctx*, double*, size_t, size_t, double*, double*, int);
 template int stage2_chase<float>(Ctx*, float*, size_t, size_t, float*, float*);
 template int stage2_chase<double>(Ctx*, double*, size_t, size_t, double*, double*);
 

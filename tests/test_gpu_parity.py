@@ -298,17 +298,39 @@ def test_cli_check_mode(capi, tname):
 
 
 # ------------------------------------------------------------------ batched (config 5 shape) --------
-@pytest.mark.parametrize("suf,count,n,b", [("f64", 24, 256, 32), ("f32", 10, 128, 16)])
+@pytest.mark.parametrize("suf,count,n,b", [("f64", 24, 256, 32), ("f32", 10, 128, 16), ("f64", 3, 1024, 64), ("f64", 2, 1280, 64)])
 def test_batched_svdvals(capi, suf, count, n, b):
-    """Many small matrices sharded over the handle's stream pool: sigma == sigma of each matrix's band."""
+    """Many small matrices, every kernel launched once per step for the whole batch (cluster per matrix, grid slice
+    per matrix, CTA group per matrix): sigma agrees with the one-matrix-at-a-time chain to the path's tolerance
+    (the batched kernels tile and reduce differently, so the results are not bit-identical)."""
     a = np.stack([uniform_matrix(n, n, 586 + i, 0.0, 5.0, DT[suf]) for i in range(count)])
     with handle(capi, n, b, suf) as h:
         sig = h.svdvals_batched(a, b)
         # reference: the same chain, one matrix at a time
         for i in (0, count // 2, count - 1):
             s1, _ = h.svdvals(a[i], b)
-            assert np.array_equal(sig[i], s1)
+            # n > 512: the reference's stage-2 schedule amplifies rounding differences of stage 1 (SURVEY 0.7), and the
+            # batched kernels round differently from the single-matrix ones
+            tol = TOL[suf] if n <= 512 else 1e-6
+            assert np.abs(sig[i].astype(np.float64) - s1.astype(np.float64)).max() <= tol * float(s1[0])
     assert np.all(np.diff(sig, axis=1) <= 0)
+
+
+@pytest.mark.parametrize("suf,count,n,b", [("f64", 300, 64, 32), ("f64", 5, 512, 64), ("f32", 40, 256, 32), ("f64", 7, 96, 32)])
+def test_batched_svdvals_vs_oracle_chain(capi, oracle, suf, count, n, b):
+    """batched path vs the CPU oracle chain (panel-order stage 1 -> stage 2) + LAPACK on the oracle's bidiagonal"""
+    a = np.stack([uniform_matrix(n, n, 1000 + i, 0.0, 5.0, DT[suf]) for i in range(count)])
+    with handle(capi, n, b, suf) as h:
+        sig = h.svdvals_batched(a, b)
+    for i in (0, count - 1):
+        band = oracle.brd_p1_panel(a[i], b)
+        _, d, e = oracle.brd_p2(band, b)
+        ref = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+        # double: gated at the path's tolerance.  float: the reference's stage-2 schedule amplifies fp32 rounding
+        # differences of stage 1 to the 1e-3 level -- its own -O3 build differs from its -O2 build by 1.4e-3 at
+        # n = 512 (SURVEY 8c: chain-level float diffs are reported, not gated at 1e-4) -- so float is gated at 5e-3.
+        tol = TOL[suf] if suf == "f64" else 5e-3
+        assert np.abs(sig[i].astype(np.float64) - ref).max() <= tol * ref[0]
 
 
 # ------------------------------------------------------------------ bisection solver ------------------
