@@ -120,6 +120,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
     uint32_t r;
@@ -134,6 +142,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Shared-memory matrix descriptor, SWIZZLE_128B (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):
 // bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
 // [46,48) version = 1 (sm_100), [61,64) layout type = 2.
+//   (kind::tf32 reads fp32 words and ignores their low 13 mantissa bits: truncation, not rounding.)
 //   K-major operand : rows of 128 B (32 tf32 along K), 8-row groups SBO apart; one MMA (K = 8) reads 32 B
 //                     of every row, the k-step advances the start address by 32 B inside the swizzle atom.
 //   MN-major operand: see make_desc_mn.
@@ -452,7 +461,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, B, MODE, 1);
+            // kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (probed: tools/tc05_selftest.py rounding), so
+            // the raw tile IS the hi operand.  [Xh | Xl] are adjacent with one slab stride: A_raw x [Xh | Xl] is one MMA
+            // of N = 2B (hi*hi -> columns [0,B), hi*lo -> [B,2B)); A_lo x Xh adds to [B,2B).
+            constexpr uint32_t idesc2 = make_idesc(128, 2 * B, MODE, 1);
+            constexpr uint32_t idesc1 = make_idesc(128, B, MODE, 1);
             for (int i = 0; i < nk; ++i) {
                 const int st = i % S;
                 const int p = i / kPeriod, buf = p & 1;
@@ -462,7 +475,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
                 tc_fence_after();
                 const uint32_t dHi = tmem + buf * (2 * B), dLo = dHi + B;
                 const uint32_t sA = base + st * Cfg::kStage, sAl = sA + Cfg::kABytes;
-                const uint32_t sXh = sA + 2 * Cfg::kABytes, sXl = sXh + Cfg::kXBytes;
+                const uint32_t sXh = sA + 2 * Cfg::kABytes;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     uint64_t ah, al;
@@ -473,37 +486,31 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
                         ah = make_desc_mn(sA + ks * 1024, 4096);
                         al = make_desc_mn(sAl + ks * 1024, 4096);
                     }
-                    const uint64_t xh = make_desc_mn(sXh + ks * 1024, 4096);
-                    const uint64_t xl = make_desc_mn(sXl + ks * 1024, 4096);
-                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-                    mma_tf32(dLo, al, xh, idesc, acc);
-                    mma_tf32(dLo, ah, xl, idesc, 1);
-                    mma_tf32(dHi, ah, xh, idesc, acc);
+                    const uint64_t xx = make_desc_mn(sXh + ks * 1024, 4096);
+                    mma_tf32(dHi, ah, xx, idesc2, (first && ks == 0) ? 0u : 1u);
+                    mma_tf32(dLo, al, xx, idesc1, 1u);
                 }
                 mma_commit(bEmpty + 8 * st);
                 if ((i % kPeriod) == kPeriod - 1 || i == nk - 1) mma_commit(bAccFull + 8 * buf);
             }
         }
     } else if (warp < 6) {
-        // ---- split: raw fp32 tile -> hi = rna_tf32(x) (in place) + lo = rna_tf32(x - hi) (second buffer, same layout) ----
+        // ---- split: lo = rna_tf32(x - trunc_tf32(x)) into the second buffer (same layout); the raw tile serves as hi ----
         const int tid = threadIdx.x - 64;
         for (int i = 0; i < nk; ++i) {
             const int st = i % S;
             mbar_wait(bFull + 8 * st, (i / S) & 1);
-            uint4* a = reinterpret_cast<uint4*>(gbase + st * Cfg::kStage);
+            const uint4* a = reinterpret_cast<const uint4*>(gbase + st * Cfg::kStage);
             uint4* al = reinterpret_cast<uint4*>(gbase + st * Cfg::kStage + Cfg::kABytes);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int idx = tid + q * 128;
-                uint4 x = a[idx];
-                uint4 h, l;
-                h.x = rna_tf32(__uint_as_float(x.x)); h.y = rna_tf32(__uint_as_float(x.y));
-                h.z = rna_tf32(__uint_as_float(x.z)); h.w = rna_tf32(__uint_as_float(x.w));
-                l.x = rna_tf32(__uint_as_float(x.x) - __uint_as_float(h.x));
-                l.y = rna_tf32(__uint_as_float(x.y) - __uint_as_float(h.y));
-                l.z = rna_tf32(__uint_as_float(x.z) - __uint_as_float(h.z));
-                l.w = rna_tf32(__uint_as_float(x.w) - __uint_as_float(h.w));
-                a[idx] = h;
+                const uint4 x = a[idx];
+                uint4 l;
+                l.x = rna_tf32(__uint_as_float(x.x) - __uint_as_float(x.x & 0xffffe000u));
+                l.y = rna_tf32(__uint_as_float(x.y) - __uint_as_float(x.y & 0xffffe000u));
+                l.z = rna_tf32(__uint_as_float(x.z) - __uint_as_float(x.z & 0xffffe000u));
+                l.w = rna_tf32(__uint_as_float(x.w) - __uint_as_float(x.w & 0xffffe000u));
                 al[idx] = l;
             }
             fence_proxy_async();
@@ -782,11 +789,18 @@ static int gemm_common(Ctx* c, int mode, const float* cm, size_t ldc, int M, int
     const int ktot = mode == 0 ? N : M;
     const int tiles = ((mode == 0 ? M : N) + 127) / 128;
     const size_t out_elems = (size_t)(mode == 0 ? M : N) * B;
-    int splits = c->num_sms / tiles;
+    // split-K so that tiles x splits fills whole waves of one CTA per SM: minimise ceil(tiles*s / SMs) / s
     const int kiters = (ktot + 31) / 32;
-    if (splits > kiters / 8) splits = kiters / 8;
-    if ((size_t)splits * out_elems > c->wpart_elems) splits = (int)(c->wpart_elems / out_elems);
-    if (splits < 1) splits = 1;
+    int smax = kiters / 16;                               // >= 512 k per split
+    if (smax > 16) smax = 16;
+    if ((size_t)smax * out_elems > c->wpart_elems) smax = (int)(c->wpart_elems / out_elems);
+    if (smax < 1) smax = 1;
+    int splits = 1;
+    double best = 1e30;
+    for (int sp = 1; sp <= smax; ++sp) {
+        const double cost = (double)((tiles * sp + c->num_sms - 1) / c->num_sms) / sp + 0.004 * sp;
+        if (cost < best - 1e-12) { best = cost; splits = sp; }
+    }
     int klen = (((ktot + splits - 1) / splits + 31) / 32) * 32;
     splits = (ktot + klen - 1) / klen;
     float* out = splits == 1 ? w : reinterpret_cast<float*>(c->wpart);

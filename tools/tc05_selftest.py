@@ -88,5 +88,38 @@ def main():
     return 0 if ok else 1
 
 
+
+
+def probe_rounding():
+    """How does kind::tf32 treat the low 13 mantissa bits of an fp32 operand in shared memory: truncation or rounding?"""
+    h = capi.Handle(256, 64, np.float32)
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((128, 32)).astype(np.float32)
+    B = rng.standard_normal((32, 64)).astype(np.float32)
+
+    def trunc(x):
+        return (x.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+
+    def rna(x):
+        u = x.view(np.uint32).astype(np.uint64) + 0x1000
+        return (u & 0xffffe000).astype(np.uint32).view(np.float32)
+
+    a = torch.from_numpy(A.copy()).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(B.T).copy()).cuda()
+    out = torch.zeros(128 * 64 + 1, device="cuda")
+    dump = torch.zeros(6144, device="cuda")
+    capi.lib().svdb200_tc05_selftest(h.h, ctypes.c_int(0), ctypes.c_int(0), ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                     ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(dump.data_ptr()))
+    torch.cuda.synchronize()
+    D = out.cpu().numpy()[:128 * 64].reshape(128, 64).astype(np.float64)
+    for name, f in (("truncate", trunc), ("round-nearest", rna), ("exact fp32", lambda x: x)):
+        ref = f(A).astype(np.float64) @ f(B).astype(np.float64)
+        print(f"model {name:14s}: max |D - ref| = {np.abs(D - ref).max():.3e}", flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "rounding":
+    probe_rounding()
+    sys.exit(0)
+
 if __name__ == "__main__":
     sys.exit(main())
