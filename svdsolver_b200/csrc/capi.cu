@@ -446,6 +446,7 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     SVDB_CREATE_CHECK(cudaMalloc(&c->s, es * band * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->tau, es * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->red, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));
+    SVDB_CREATE_CHECK(cudaMemset(c->red, 0, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));   // flag-stamped words start unset
     SVDB_CREATE_CHECK(cudaMalloc(&c->bar, 64));
     SVDB_CREATE_CHECK(cudaMemset(c->bar, 0, 64));
     SVDB_CREATE_CHECK(cudaMalloc(&c->prog, sizeof(int) * (max_n + 8)));
@@ -673,6 +674,8 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
     if (kind == 4) return probe_tc05_tf32(c, tflops);
     return probe_peak(c, kind, tflops);
 }
+
+int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
 
 int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit) {
     if (!h || method < 0 || method > 2) return SVDB200_E_ARG;

@@ -34,6 +34,7 @@ struct Ctx {
     size_t wpart_elems = 0;
     void* s = nullptr;             // band * band   : S (= -T of compact WY), upper triangular
     void* tau = nullptr;           // band
+    unsigned panel_epoch = 0;      // sequence base of the flag-stamped panel all-reduce words (one per launch)
     void* red = nullptr;           // panel all-reduce scratch: 2 * kMaxPanelCtas * (2*band + 8)
     unsigned int* bar = nullptr;   // software grid barrier state (2 words) + misc counters
     int* prog = nullptr;           // stage-2 per-sweep progress counters (max_n)
@@ -196,6 +197,7 @@ template <typename T> int mse_metric(Ctx* c, const T* a, const T* b, size_t n, s
 template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma);
 int probe_peak(Ctx* c, int kind, double* tflops);
 int probe_tc05_tf32(Ctx* c, double* tflops);
+int panel_reg_debug_read(long long* out16);
 int tc05_selftest(Ctx* c, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);
 
 }  // namespace svdb200

@@ -6,8 +6,10 @@
 //   * the pivot column is broadcast inside the warp with shuffles, so the rank-1 update of column j
 //     and the dot products needed for column j+1 are ONE fused pass over the registers
 //     (the shared-memory version makes two passes per column and was bound by their latency);
-//   * per column: one cross-warp reduction, one all-reduce across CTAs (DSMEM + barrier.cluster for
-//     clusters of <= 16 CTAs, L2 + software grid barrier otherwise), scalars recomputed per thread.
+//   * per column: one cross-warp reduction, one all-reduce across CTAs, scalars recomputed per thread.  The
+//     all-reduce is two-level: DSMEM + barrier.cluster inside a cluster of <= 16 CTAs; panels taller than one
+//     cluster run as several clusters whose per-cluster vectors cross L2 once, stamped with a release flag
+//     (no grid barrier, 8 x b values to read instead of G x b).  The L2-only grid transport remains as fallback.
 // Shared memory is only used for the reductions, the transposed load/store of LQ row panels and the
 // epilogue (V, V2 = V S^T by back substitution with T^-1 = D + striu(V^T V), R/L write-back).
 #include <cooperative_groups.h>
@@ -18,7 +20,50 @@ namespace cg = cooperative_groups;
 namespace svdb200 {
 namespace {
 
-constexpr int kThreads = 256, kWarps = 8;
+constexpr int kThreads = 256, kWarps = 8;     // two CTAs per SM: eight 16-CTA clusters (128 CTAs) can be co-resident
+constexpr int kMaxClusters = 18;      // clusters per panel launch (two-level all-reduce)
+
+#ifndef SVDB_PANEL_TIMING
+#define SVDB_PANEL_TIMING 0
+#endif
+// per-phase cycle counters of CTA 0 / thread 0 (debug builds only: -DSVDB_PANEL_TIMING=1)
+__device__ long long g_panel_dbg[16];
+#define PANEL_TICK(k)                                                        \
+    do {                                                                     \
+        if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) {      \
+            long long _t = clock64();                                        \
+            g_panel_dbg[k] += _t - tick;                                     \
+            tick = _t;                                                       \
+        }                                                                    \
+    } while (0)
+
+// Flag-stamped words (the "LL" idea): every 8-byte half carries 32 data bits and the 32-bit sequence number of the
+// column it belongs to, so a reader that sees the expected number in both halves has the data -- one L2 round trip,
+// no separate flag, no fence.  Entries are 16 bytes for both element types (float uses the first half).
+template <typename T> struct LLWord;
+template <> struct LLWord<float> {
+    static __device__ __forceinline__ void store(void* p, float v, unsigned seq) {
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+    }
+    static __device__ __forceinline__ bool try_load(const void* p, unsigned seq, float& v) {
+        unsigned a, b;
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+        v = __uint_as_float(a);
+        return b == seq;
+    }
+};
+template <> struct LLWord<double> {
+    static __device__ __forceinline__ void store(void* p, double v, unsigned seq) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)u), "r"(seq), "r"((unsigned)(u >> 32)), "r"(seq) : "memory");
+    }
+    static __device__ __forceinline__ bool try_load(const void* p, unsigned seq, double& v) {
+        unsigned a, b, c2, d;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "l"(p) : "memory");
+        v = __longlong_as_double((long long)(((unsigned long long)c2 << 32) | a));
+        return b == seq && d == seq;
+    }
+};
 
 template <typename T, int CPL>
 __device__ __forceinline__ T pick(const T (&v)[CPL], int u) {
@@ -31,11 +76,16 @@ __device__ __forceinline__ T pick(const T (&v)[CPL], int u) {
 template <typename T, bool kTrans, bool kCluster, int RPT, int CPL>
 __global__ void __launch_bounds__(kThreads)
 panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, T* __restrict__ red,
-                 unsigned* __restrict__ bar) {
+                 unsigned* __restrict__ bar, int NC, unsigned epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int ROWS = RPT * kWarps;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, w = tid >> 5;
     const int G = gridDim.x, g = blockIdx.x;
+    // kCluster: NC clusters of CS = G / NC CTAs.  The all-reduce of a column is two-level: DSMEM inside a cluster
+    // (barrier.cluster), then -- only when NC > 1 -- one flag-stamped vector per cluster through L2.
+    const int CS = kCluster ? G / max(NC, 1) : G;
+    const int cl = kCluster ? g / CS : 0, crank = kCluster ? g - cl * CS : g;
+    (void)cl; (void)crank;
     const int r0 = g * ROWS;
     const int R = max(0, min(ROWS, m - r0));
     const int ld = b + 1, slot = 2 * b;
@@ -92,7 +142,10 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     }
     __syncthreads();
 
+    long long tick = SVDB_PANEL_TIMING ? clock64() : 0;
+    (void)tick;
     for (int j = 0; j < kmax; ++j) {
+        PANEL_TICK(0);
         // ---- cross-warp reduction of the local dots, publication -----------------------------------------
 #pragma unroll
         for (int u = 0; u < CPL; ++u) if (valid[u]) psum[w * b + cu[u]] = acc[u];
@@ -112,6 +165,7 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             }
         }
         __syncthreads();
+        PANEL_TICK(1);
         for (int c = tid; c < b; c += nt) {
             T s = psum[c];
 #pragma unroll
@@ -119,35 +173,92 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             if (kCluster) mine[c] = s; else st_cg(&mine[c], s);
         }
         if (kCluster) cg::this_cluster().sync(); else grid_barrier(bar, (unsigned)G, gen);
+        PANEL_TICK(2);
         // ---- all-reduce across CTAs in a fixed association -------------------------------------------------
         {
-            const int chunk = (G + rgroups - 1) / rgroups;
-            const int jowner = j / ROWS;
-            if (in2d) {
-                const int c = tx, part = tyy;
-                const int q0 = part * chunk, q1 = min(G, q0 + chunk);
-                T s = (T)0;
-                if (kCluster) {
-                    cg::cluster_group cl = cg::this_cluster();
+            const int jowner = j / ROWS;                 // CTA that holds global row j
+            if (kCluster) {
+                // level 1: the CS partial vectors of this cluster, read over DSMEM
+                const int chunk = (CS + rgroups - 1) / rgroups;
+                if (in2d) {
+                    const int c = tx, part = tyy;
+                    const int q0 = part * chunk, q1 = min(CS, q0 + chunk);
+                    T s = (T)0;
+                    cg::cluster_group clg = cg::this_cluster();
 #pragma unroll 4
-                    for (int q = q0; q < q1; ++q) s += cl.map_shared_rank(lred, q)[(j & 1) * slot + c];
-                    if (part == 0) piv[c] = cl.map_shared_rank(lred, jowner)[(j & 1) * slot + b + c];
-                } else {
+                    for (int q = q0; q < q1; ++q) s += clg.map_shared_rank(lred, q)[(j & 1) * slot + c];
+                    if (part == 0 && jowner / CS == cl) piv[c] = clg.map_shared_rank(lred, jowner - cl * CS)[(j & 1) * slot + b + c];
+                    psum[part * b + c] = s;
+                }
+                __syncthreads();
+                PANEL_TICK(3);
+                if (tid < b) {                            // nt >= b: thread c owns column c of the reduced vectors
+                    const int c = tid;
+                    T s = psum[c];
+                    for (int part = 1; part < rgroups; ++part) s += psum[part * b + c];
+                    if (NC > 1) {
+                        // level 2: rank 0 of every cluster publishes the cluster's vector (and the pivot row when the
+                        // cluster owns it) as flag-stamped words; thread c of every CTA collects the NC words of its
+                        // column and adds them in cluster order.  Slots alternate with the column parity; a cluster can
+                        // only be one column ahead of the slowest one, so a slot is never overwritten while still read.
+                        const unsigned seq = epoch * 128u + (unsigned)(j + 1);
+                        char* gs = reinterpret_cast<char*>(red) + (size_t)(j & 1) * NC * slot * 16;
+                        const int ocl = jowner / CS;
+                        if (crank == 0) {
+                            LLWord<T>::store(gs + ((size_t)cl * slot + c) * 16, s, seq);
+                            if (ocl == cl) LLWord<T>::store(gs + ((size_t)cl * slot + b + c) * 16, piv[c], seq);
+                        }
+                        PANEL_TICK(4);
+                        T v[kMaxClusters], pv = (T)0;
+                        unsigned pending = (1u << NC) - 1u;
+                        bool pdone = false;
+                        unsigned polls = 0;
+                        unsigned long long t0 = 0;
+                        while (pending != 0u || !pdone) {
+                            if ((++polls & 4095u) == 0u) {       // a cluster that never becomes resident must not hang the GPU
+                                unsigned long long now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > 4000000000ull) __trap();
+                            }
+#pragma unroll
+                            for (int q = 0; q < kMaxClusters; ++q)
+                                if ((pending >> q) & 1u) {
+                                    if (LLWord<T>::try_load(gs + ((size_t)q * slot + c) * 16, seq, v[q])) pending &= ~(1u << q);
+                                }
+                            if (!pdone) pdone = LLWord<T>::try_load(gs + ((size_t)ocl * slot + b + c) * 16, seq, pv);
+                            if (pending != 0u || !pdone) __nanosleep(100);   // back off: the update kernels beside us are L2 / HBM bound
+                        }
+                        PANEL_TICK(5);
+                        s = v[0];
+#pragma unroll
+                        for (int q = 1; q < kMaxClusters; ++q) if (q < NC) s += v[q];
+                        piv[c] = pv;
+                    }
+                    zs[c] = s;
+                }
+            } else {
+                const int chunk = (G + rgroups - 1) / rgroups;
+                if (in2d) {
+                    const int c = tx, part = tyy;
+                    const int q0 = part * chunk, q1 = min(G, q0 + chunk);
+                    T s = (T)0;
                     const T* buf = red + (size_t)(j & 1) * (G + 1) * slot;
 #pragma unroll 8
                     for (int q = q0; q < q1; ++q) s += ld_cg(&buf[(size_t)q * slot + c]);
                     if (part == 0) piv[c] = ld_cg(&buf[(size_t)G * slot + c]);
+                    psum[part * b + c] = s;
                 }
-                psum[part * b + c] = s;
-            }
-            __syncthreads();
-            for (int c = tid; c < b; c += nt) {
-                T s = psum[c];
-                for (int part = 1; part < rgroups; ++part) s += psum[part * b + c];
-                zs[c] = s;
+                __syncthreads();
+                for (int c = tid; c < b; c += nt) {
+                    T s = psum[c];
+                    for (int part = 1; part < rgroups; ++part) s += psum[part * b + c];
+                    zs[c] = s;
+                }
             }
         }
         __syncthreads();
+        PANEL_TICK(6);
         // ---- scalars (every thread), Gram column ---------------------------------------------------------------
         const T x0 = piv[j];
         const T nrm = sqrt(zs[j] + x0 * x0);
@@ -165,6 +276,38 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 if (valid[u] && cu[u] < j) Gm[cu[u] * b + j] = piv[cu[u]] + alpha * zs[cu[u]];
             if (lane == 0) taus[j] = tau;
         }
+        if (sizeof(T) == 8) {
+        // ---- fused pass: rank-1 update of column j, dots for column j+1 ---------------------------------------
+        // Branch-free: per-lane column predicates become factors (fm = 0 for finished columns), per-row predicates
+        // become a zero reflector entry, so every (row, column) is one FMA for the update, one select for the
+        // column that becomes v_j, and one FMA for the dot products.
+        const int lj = j & 31, uj = j >> 5, ln = (j + 1) & 31, un = (j + 1) >> 5;
+        const bool more = (j + 1 < kmax);
+        T fm[CPL];
+        bool isj[CPL];
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) { fm[u] = (cu[u] > j) ? fsr[u] : (T)0; isj[u] = (cu[u] == j); acc[u] = (T)0; }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int rl = w + kWarps * i;
+            const int grow = r0 + rl;
+            const T xj = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i], uj), lj);
+            const bool act = (rl < R) && (grow >= j);
+            const T wv = act ? ((grow == j) ? (T)1 : xj * alpha) : (T)0;
+            const T cj = (grow == j) ? beta : wv;
+#pragma unroll
+            for (int u = 0; u < CPL; ++u) {
+                const T nv = a[i][u] - wv * fm[u];
+                a[i][u] = (isj[u] && act) ? cj : nv;
+            }
+            if (more) {
+                const T pn = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i], un), ln);
+                const T pe = ((rl < R) && (grow > j + 1)) ? pn : (T)0;
+#pragma unroll
+                for (int u = 0; u < CPL; ++u) acc[u] += a[i][u] * pe;
+            }
+        }
+        } else {
         // ---- fused pass: rank-1 update of column j, dots for column j+1 ---------------------------------------
         const int lj = j & 31, uj = j >> 5, ln = (j + 1) & 31, un = (j + 1) >> 5;
         const bool more = (j + 1 < kmax);
@@ -191,9 +334,12 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 }
             }
         }
+        }
         // psum / zs / piv are rewritten only after the next __syncthreads-protected phases
         __syncthreads();
+        PANEL_TICK(7);
     }
+    PANEL_TICK(8);
 
     // ---- epilogue ------------------------------------------------------------------------------------------
 #pragma unroll
@@ -242,6 +388,7 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             for (int rl = lane; rl < R; rl += 32) V2[(size_t)c * m + (r0 + rl)] = Ps[rl * ld + c];
     }
     if (kCluster) cg::this_cluster().sync();
+    PANEL_TICK(9);
 }
 
 inline size_t reg_smem_bytes(int rows, int b, size_t esz) {
@@ -256,39 +403,66 @@ int launch_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
     const size_t smem = reg_smem_bytes(ROWS, b, sizeof(T));
     T* red = reinterpret_cast<T*>(c->red);
     unsigned* bar = c->bar;
-    if (c->cluster_ok && G <= c->cluster_ok) {
+    if (c->cluster_ok) {
+        // clusters of CS CTAs; more than one cluster when the panel is taller than CS * ROWS rows (two-level all-reduce).
+        // All clusters of a launch must be co-resident (they wait for each other's words): ask the occupancy API.
         auto kern = panel_reg_kernel<T, kTrans, true, RPT, CPL>;
         SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (G > 8) SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(G);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = G;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, red, bar);
-        if (e == cudaSuccess) { c->launches++; return 0; }
-        cudaGetLastError();
-        c->cluster_ok = c->cluster_ok > 8 ? 8 : 0;
-        return launch_reg<T, kTrans, RPT, CPL>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (c->cluster_ok > 8) SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const int cands[2] = {c->cluster_ok, c->cluster_ok > 8 ? 8 : 0};
+        for (int t = 0; t < 2; ++t) {
+            const int cs_try = cands[t];
+            if (cs_try <= 0) continue;
+            const int CS = G <= cs_try ? G : cs_try;
+            const int NC = (G + CS - 1) / CS;
+            if (NC > kMaxClusters) continue;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(NC * CS);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = CS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (NC > 1) {
+                // the occupancy query costs ~0.1 ms of host time: once per (cluster size, shared-memory size)
+                static int cache_cs[8], cache_smem[8], cache_val[8], cache_n = 0;
+                int max_clusters = -1;
+                for (int q = 0; q < cache_n; ++q)
+                    if (cache_cs[q] == CS && cache_smem[q] == (int)smem) max_clusters = cache_val[q];
+                if (max_clusters < 0) {
+                    max_clusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
+                    if (cache_n < 8) { cache_cs[cache_n] = CS; cache_smem[cache_n] = (int)smem; cache_val[cache_n] = max_clusters; ++cache_n; }
+                }
+                if (NC > max_clusters) continue;
+            }
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, red, bar, NC, ++c->panel_epoch);
+            if (e == cudaSuccess) { c->launches++; return 0; }
+            cudaGetLastError();
+            if (NC == 1) {                     // cluster shape not schedulable here: smaller clusters, then the grid transport
+                c->cluster_ok = c->cluster_ok > 8 ? 8 : 0;
+                return launch_reg<T, kTrans, RPT, CPL>(c, a, lda, m, b, V, V2, stream, cooperative);
+            }
+        }
     }
     auto kern = panel_reg_kernel<T, kTrans, false, RPT, CPL>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), stream));
+    int nc0 = 0;
     if (cooperative) {
-        void* args[] = {&a, &lda, &m, &b, &V, &V2, &red, &bar};
+        unsigned ep0 = 0;
+        void* args[] = {&a, &lda, &m, &b, &V, &V2, &red, &bar, &nc0, &ep0};
         SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kThreads), args, smem, stream));
     } else {
         // look-ahead panels run beside the trailing update: a cooperative launch is gang-scheduled
         // and would wait for the update to drain; G <= #SMs CTAs of this size always become
         // co-resident once the update's CTAs retire, so the software barrier still completes.
-        kern<<<G, kThreads, smem, stream>>>(a, lda, m, b, V, V2, red, bar);
+        kern<<<G, kThreads, smem, stream>>>(a, lda, m, b, V, V2, red, bar, nc0, 0u);
         SVDB_CHECK(c, cudaGetLastError());
     }
     c->launches++;
@@ -297,11 +471,31 @@ int launch_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
 
 }  // namespace
 
+// debug: read (and clear) the per-phase cycle counters of the timing build
+int panel_reg_debug_read(long long* out16) {
+    long long z[16] = {};
+    if (cudaMemcpyFromSymbol(out16, g_panel_dbg, sizeof(z)) != cudaSuccess) return 1;
+    cudaMemcpyToSymbol(g_panel_dbg, z, sizeof(z));
+    return 0;
+}
+
 // returns 0 when it ran, 1 when the shape is outside this kernel's range (caller falls back)
 template <typename T, bool kTrans>
 int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream, bool cooperative) {
-    if (b <= 32) return launch_reg<T, kTrans, 32, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
-    if (b <= 64) return launch_reg<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+    // rows per CTA = 8 * RPT: the smallest slice that still fits the panel into 128 co-resident CTAs (eight 16-CTA
+    // clusters), so that the per-column register pass shrinks with the panel height
+    // (double only: in float the column loop is bound by the exchange, and more CTAs only add participants)
+    const int cap = sizeof(T) == 8 ? 128 : 0;
+    if (b <= 32) {
+        if (m <= cap * 64) return launch_reg<T, kTrans, 8, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (m <= cap * 128) return launch_reg<T, kTrans, 16, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
+        return launch_reg<T, kTrans, 32, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
+    }
+    if (b <= 64) {
+        if (m <= cap * 32) return launch_reg<T, kTrans, 4, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (m <= cap * 64) return launch_reg<T, kTrans, 8, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+        return launch_reg<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+    }
     return 1;
 }
 template int launch_panel_reg<float, false>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t, bool);
