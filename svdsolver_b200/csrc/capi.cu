@@ -438,6 +438,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (la && la[0] == '0') c->lookahead = 0;
         const char* pr = getenv("SVDB200_PANEL_REG");
         if (pr && pr[0] == '0') c->panel_reg = 0;
+        const char* prm = getenv("SVDB200_PANEL_REG_MIN");
+        if (prm && prm[0]) c->panel_reg_min = atoi(prm);
     }
     SVDB_CREATE_CHECK(cudaMalloc(&c->w, es * nb * band));
     c->wpart_elems = 16 * nb * band;

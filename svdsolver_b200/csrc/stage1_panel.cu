@@ -250,7 +250,7 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
     if (!V2) V2 = reinterpret_cast<T*>(c->v2);
     // register-resident kernel for tall panels (grid transport); cluster-sized panels are issue-bound
     // either way and stay on the shared-memory kernel below
-    if (c->panel_reg && m > 16 * 256) {
+    if (c->panel_reg && m > c->panel_reg_min) {
         int st = launch_panel_reg<T, kTrans>(c, a, lda, m, b, V, V2, stream, stream == c->stream);
         if (st != 1) return st;
     }

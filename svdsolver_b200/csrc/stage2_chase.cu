@@ -38,17 +38,15 @@ __host__ __device__ inline int stage2_threads(int c) {
     return ((need + 31) / 32) * 32;
 }
 
-// Poll a progress counter with relaxed loads (an acquire load per poll would invalidate the L1
-// every time: CCTL.IVALL), then take ONE acquire load of the same counter to order the reads that
-// follow (cheaper than fence.acq_rel.gpu, which also drains this thread's outstanding stores).
-__device__ __forceinline__ void wait_progress(const int* p, int need) {
+// Wait until the predecessor sweep has completed `need` window ops.  `seen` caches the last value read from its
+// counter: counters only grow, so when the predecessor is already far enough ahead no memory access is needed at all
+// (two L2 round trips per op otherwise).  The poll itself is an acquire load: everything the CTA reads from other
+// CTAs afterwards goes through L2 (ld.global.cg), so the L1 invalidation an acquire implies costs nothing here.
+__device__ __forceinline__ int wait_progress(const int* p, int need, int seen) {
+    if (seen >= need) return seen;
     int v;
-    while (true) {
-        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-        if (v >= need) break;
-        __nanosleep(20);
-    }
-    (void)ld_acquire(p);
+    while ((v = ld_acquire(p)) < need) __nanosleep(20);
+    return v;
 }
 
 // Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.
@@ -165,7 +163,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
     for (int mat = grp; mat < count; mat += ngroups) {
     T* __restrict__ A = A0 + (size_t)mat * N * N;
     int* __restrict__ prog = prog0 + (size_t)mat * N;
+    const int rel_tid = nt > 32 ? 32 : 0;                   // the progress counter is published by a thread off thread 0's path
     for (int i = rank; i < n - 1; i += G) {
+        int seen = 0;                                         // last observed progress of sweep i-1 (thread 0 only)
         const int top_j2 = min(i + 2 * w - 1, n);
         const int npairs = 1 + (n - top_j2) / c + 1;
         int fr = 0;                               // rows of the forwarded block sitting in WR (0: none)
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
             {
                 const int q = 2 * p;
                 if (i > 0) {
-                    if (tid == 0) wait_progress(&prog[i - 1], q + 4);
+                    if (tid == 0) seen = wait_progress(&prog[i - 1], q + 4, seen);
                     __syncthreads();
                 }
                 const int nc = r2 - r1, nr = r2 - r0;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                                       else WL[(r - keep) * ldl + cc] = v;
                                   });
                 __syncthreads();
-                if (tid == 0) st_release(&prog[i], q + 1);
+                if (tid == rel_tid) st_release(&prog[i], q + 1);
             }
             // ================= LEFT(p): rows [r1,r2) x cols [r1,c3), window = [F | N] ====================
             const int nn = c3 - r2;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
             {
                 const int q = 2 * p + 1;
                 if (i > 0) {
-                    if (tid == 0) wait_progress(&prog[i - 1], q + 4);
+                    if (tid == 0) seen = wait_progress(&prog[i - 1], q + 4, seen);
                     __syncthreads();
                 }
                 const int nr = r2 - r1, fc = r2 - r1, nc = fc + nn;
@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                                   });
                 fr = fwd ? nr : 0;
                 __syncthreads();
-                if (tid == 0 && fwd) st_release(&prog[i], q + 1);
+                if (tid == rel_tid && fwd) st_release(&prog[i], q + 1);
             }
             if (!fwd) break;
         }
-        if (tid == 0) st_release(&prog[i], INT_MAX);
+        if (tid == rel_tid) st_release(&prog[i], INT_MAX);
     }
     }
 }
