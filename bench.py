@@ -42,6 +42,11 @@ METRIC = "bidiag_reduction_gflops"
 UNIT = "GFLOP/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one stage2_chase_kernel<double> launch at n = 3840, band 32 from the
+# committed ncu --set full capture (profiles/); None until measured
+S2_TRAFFIC = 4479488   # 3.477 MB read + 1.002 MB written (profiles/r01_summary.md, prof_r1_s2c)
+
+
 def flops(n):
     return 8.0 * n ** 3 / 3.0
 
@@ -210,6 +215,68 @@ def north_star_shape(capi, torch, stream, dev, local_rank, dt, peaks, hbm_peak, 
         return {"error": str(ex)}
 
 
+def full_configs(capi, torch, stream, dev, local_rank):
+    """BASELINE configs[2] (n=16384 double full SVD, band 64) and one GPU's share of configs[4] (1024 of the 8192 batched
+    256x256 double SVDs, band 32): device time per stage, CUDA events on the launching stream."""
+    out = {}
+    try:
+        n, b = 16384, 64
+        h = capi.Handle(n, b, np.float64, device=local_rank)
+        h.set_stream(stream.cuda_stream)
+        a = torch.empty(n, n, device=dev, dtype=torch.float64)
+        d = torch.empty(n, device=dev, dtype=torch.float64)
+        e = torch.empty(n, device=dev, dtype=torch.float64)
+        sg = torch.empty(n, device=dev, dtype=torch.float64)
+        h.fill_uniform_dev(a.data_ptr(), n * n, 586 + n, 0.0, 5.0)
+        fro = float(torch.linalg.norm(a))
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        h.dense_to_band_dev(a.data_ptr(), n, b)
+        ev[1].record(stream)
+        h.band_to_bidiag_dev(a.data_ptr(), n, b, d.data_ptr(), e.data_ptr())
+        ev[2].record(stream)
+        h.bidiag_qr_dev(d.data_ptr(), e.data_ptr(), n, sg.data_ptr())
+        ev[3].record(stream)
+        torch.cuda.synchronize()
+        t1, t2, t3 = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        out["config3_full_svd"] = {"workload": "16384x16384 double full SVD (dense->band->bidiagonal->singular values), band 64, one B200",
+                                   "stage1_ms": round(t1, 1), "stage2_ms": round(t2, 1), "sigma_ms": round(t3, 1), "total_ms": round(t1 + t2 + t3, 1),
+                                   "reduction_gflops": round(flops(n) / ((t1 + t2) * 1e-3) * 1e-9, 1),
+                                   "sigma_solver": "bisection on the Golub-Kahan form (n > 1024); zero-shift QR sweeps below",
+                                   "frobenius_rel_err": abs(float(torch.sqrt((sg * sg).sum())) - fro) / fro}
+        h.close()
+        del a, d, e, sg
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["config3_full_svd"] = {"error": str(ex)}
+    try:
+        cnt, n, b = 1024, 256, 32
+        h = capi.Handle(n, b, np.float64, device=local_rank)
+        h.set_stream(stream.cuda_stream)
+        a = torch.empty(cnt, n, n, device=dev, dtype=torch.float64)
+        h.fill_uniform_dev(a.data_ptr(), cnt * n * n, 586, 0.0, 5.0)
+        a0 = a.clone()
+        sg = torch.empty(cnt, n, device=dev, dtype=torch.float64)
+        best = None
+        for rep in range(3):
+            a.copy_(a0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            h.svdvals_batched_dev(a.data_ptr(), cnt, n, b, sg.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        out["config5_batched_share"] = {"workload": "1024 x (256x256 double SVD, band 32) = one GPU's share of BASELINE configs[4] at 8 GPUs",
+                                        "ms": round(best, 1), "matrices_per_s": round(cnt / best * 1e3, 1)}
+        h.close()
+    except Exception as ex:
+        out["config5_batched_share"] = {"error": str(ex)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,7 +404,7 @@ def main():
                            "stage1_gflops": round(flops(n) / (t1 * 1e-3) * 1e-9, 1)})
 
     # ---- roofline of the dominant kernel: profiled pass, CUDA events per launch ------------------
-    roofline, prof_out, peaks, big, big32 = None, None, {}, None, None
+    roofline, prof_out, peaks, big, big32, other = None, None, {}, None, None, None
     if rank == 0:
         h = handles["f64"]
         peaks = {"dfma_tflops": h.probe_peak(0), "dmma_f64_tflops": h.probe_peak(1), "ffma_tflops": h.probe_peak(2),
@@ -371,7 +438,7 @@ def main():
             ach = v["work"] / (v["ms"] * 1e-3) * 1e-9
             peak = hbm_peak or 6650.0
             roofline = {"bound": "hbm", "kernel": "stage2_chase_kernel<double> (band -> bidiagonal bulge chasing)",
-                        "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": S2_TRAFFIC,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if hbm_peak else "fallback 6.65 TB/s",
                         "algorithmic_bytes": "4*b*n^2*sizeof(T) window bytes per launch (SURVEY 8d)",
                         "note": "dependency-latency bound by construction (4 window ops x n sweeps on the critical path, "
@@ -393,6 +460,7 @@ def main():
                 pass
             big = north_star_shape(capi, torch, stream, dev, local_rank, np.float64, peaks, hbm_peak or 6650.0)
             big32 = north_star_shape(capi, torch, stream, dev, local_rank, np.float32, peaks, hbm_peak or 6650.0)
+            other = full_configs(capi, torch, stream, dev, local_rank) if world == 1 else None
     # ---- e2e: host-pointer C-ABI call with pinned host buffers --------------------------------------
     from svdsolver_b200.synth import uniform_matrix
     e2e = None
@@ -479,7 +547,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_classes_f64": prof_out, "north_star_shape": big, "north_star_shape_f32": big32, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
+            "kernel_classes_f64": prof_out, "north_star_shape": big, "north_star_shape_f32": big32, "other_configs": other, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
         }
         print(json.dumps(line), flush=True)
     for h in handles.values():
