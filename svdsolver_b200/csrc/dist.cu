@@ -19,7 +19,7 @@
 #include "common.cuh"
 
 namespace svdb200 {
-template <typename T, bool kTrans> int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b);
+template <typename T, bool kTrans> int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
 
 namespace {
 
@@ -132,6 +132,15 @@ __global__ void scatter_local_kernel(const T* __restrict__ panel, const T* __res
     ut_loc[lc * b + r] = ut[gc * b + r];
 }
 
+// Look-ahead (same scheme as the single-GPU driver, stage1_panel.cu): the part of an update that the NEXT panel lives in
+// is applied first; the panel (and its collective) then runs on the high-priority aux stream s1 while the main stream s0
+// finishes the much larger rest of the update.
+//   s1: [QR panel k on its owner] Bcast(V) Bcast(V2)            | pack, AllGather, assemble, LQ panel (every rank), scatter
+//   s0: W = V^T A2, update of the b rows of the LQ panel ........| rest of the QR update | W = A3 U^T, AllReduce(W),
+//       update of the b columns of QR panel k+1 (its owner) -> s1 starts panel k+1 | rest of the LQ update
+// QR reflectors live in (v, v2), LQ reflectors in (vb, v2b): a panel in flight never overwrites reflectors that the
+// concurrent update still reads.  Every rank issues the collectives in the same order (Bcast, Bcast, AllGather, AllReduce
+// per step); NCCL serialises operations of one communicator across streams, which is the order the data needs anyway.
 template <typename T>
 int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
     Ctx* c = d->ctx;
@@ -140,62 +149,108 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
     const size_t ldl = svdb200_dist_local_cols(n, band, rk, P);
     T* V = reinterpret_cast<T*>(c->v);
     T* V2 = reinterpret_cast<T*>(c->v2);
+    T* Vl = reinterpret_cast<T*>(c->vb);
+    T* V2l = reinterpret_cast<T*>(c->v2b);
     T* W = reinterpret_cast<T*>(c->w);
     T* rowpanel = reinterpret_cast<T*>(d->rowpanel);
     T* gathered = reinterpret_cast<T*>(d->gather);
     T* sendbuf = reinterpret_cast<T*>(d->sendbuf);
     T* ut_loc = reinterpret_cast<T*>(d->ut_loc);
     T* u2_loc = reinterpret_cast<T*>(d->u2_loc);
-    cudaStream_t s = c->stream;
-    for (size_t k = 0; k < nb; ++k) {
+    const bool ahead = !c->profile && c->aux_stream != nullptr && c->lookahead;
+    cudaStream_t s0 = c->stream, s1 = ahead ? c->aux_stream : c->stream;
+    cudaEvent_t evQ = c->lev[1], evR = c->lev[2], evL = c->lev[3], evP = c->lev[0];
+    if (ahead) {   // the aux stream must see everything enqueued on the main stream so far
+        SVDB_CHECK(c, cudaEventRecord(evP, s0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0));
+    }
+    // QR panel 0 + broadcast
+    auto qr_panel_and_bcast = [&](size_t k) -> int {
         const size_t o = k * band, m = n - o;
         const int owner = (int)(k % P);
-        const size_t lb_panel = k / P;
-        // ---- QR half-step ------------------------------------------------------------------------------
-        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + lb_panel * band, ldl, (int)m, b)));
+        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, V, V2, s1)));
         if (P > 1) {
             // V and V2 are adjacent allocations only by accident: broadcast them separately
-            SVDB_NCCL(d, nccl().Broadcast(V, V, m * band, nccl_type<T>(), owner, d->comm, s));
-            SVDB_NCCL(d, nccl().Broadcast(V2, V2, m * band, nccl_type<T>(), owner, d->comm, s));
+            SVDB_NCCL(d, nccl().Broadcast(V, V, m * band, nccl_type<T>(), owner, d->comm, s1));
+            SVDB_NCCL(d, nccl().Broadcast(V2, V2, m * band, nccl_type<T>(), owner, d->comm, s1));
         }
+        if (ahead) SVDB_CHECK(c, cudaEventRecord(evQ, s1));
+        return 0;
+    };
+    SVDB_TRY(qr_panel_and_bcast(0));
+    for (size_t k = 0; k < nb; ++k) {
+        const size_t o = k * band, m = n - o;
+        const bool has_lq = (o + band < n - 1);
         const size_t lb0 = first_local_block_after(k, rk, P);        // first local block with global index > k
         const size_t ncl = ldl - lb0 * band;                         // local trailing columns
+        // ---- QR half-step ------------------------------------------------------------------------------
+        if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, evQ, 0));   // reflectors of panel k have arrived
+        T* A2 = a + o * ldl + lb0 * band;
         if (ncl > 0) {
-            T* A2 = a + o * ldl + lb0 * band;
             SVDB_TRY(gemm_tn<T>(c, V, A2, ldl, m, ncl, band, W));
-            SVDB_TRY(rank_update<T>(c, A2, ldl, m, ncl, band, V2, W, ncl));
+            if (has_lq) SVDB_TRY(rank_update<T>(c, A2, ldl, band, ncl, band, V2, W, ncl));               // rows of the LQ panel first
+            else SVDB_TRY(rank_update<T>(c, A2, ldl, m, ncl, band, V2, W, ncl));
+        }
+        if (!has_lq) {
+            // last steps: no LQ; the next QR panel (if any) follows directly
+            if (k + 1 < nb) {
+                if (ahead) { SVDB_CHECK(c, cudaEventRecord(evP, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0)); }
+                SVDB_TRY(qr_panel_and_bcast(k + 1));
+            }
+            continue;
         }
         // ---- LQ half-step ------------------------------------------------------------------------------
-        if (o + band < n - 1) {
-            const size_t np = n - o - band;                          // global width of the row panel
-            const size_t mr = m - band;
-            // gather the b x np row panel on every rank
-            {
-                size_t cnt = (size_t)b * d->ncl_max;
-                pack_rows_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(a + o * ldl + lb0 * band, ldl, b, ncl, d->ncl_max, sendbuf);
-                c->launches++;
-                if (P > 1) SVDB_NCCL(d, nccl().AllGather(sendbuf, gathered, cnt, nccl_type<T>(), d->comm, s));
-                else SVDB_CHECK(c, cudaMemcpyAsync(gathered, sendbuf, cnt * sizeof(T), cudaMemcpyDeviceToDevice, s));
-                size_t tot = (size_t)b * np;
-                assemble_panel_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(gathered, b, np, d->ncl_max, k, P, rowpanel);
-                c->launches++;
-            }
-            // every rank factorises the same panel: Ut (np x b) -> c->v, U2 (b x np) -> c->v2
-            SVDB_TRY((launch_panel_public<T, true>(c, rowpanel, np, (int)np, b)));
+        const size_t np = n - o - band;                              // global width of the row panel
+        const size_t mr = m - band;
+        if (ahead) { SVDB_CHECK(c, cudaEventRecord(evR, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evR, 0)); }
+        {   // s1: gather the b x np row panel on every rank, factorise it redundantly, scatter the local slices
+            size_t cnt = (size_t)b * d->ncl_max;
+            pack_rows_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s1>>>(A2, ldl, b, ncl, d->ncl_max, sendbuf);
+            c->launches++;
+            if (P > 1) SVDB_NCCL(d, nccl().AllGather(sendbuf, gathered, cnt, nccl_type<T>(), d->comm, s1));
+            else SVDB_CHECK(c, cudaMemcpyAsync(gathered, sendbuf, cnt * sizeof(T), cudaMemcpyDeviceToDevice, s1));
+            size_t tot = (size_t)b * np;
+            assemble_panel_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s1>>>(gathered, b, np, d->ncl_max, k, P, rowpanel);
+            c->launches++;
+            // every rank factorises the same panel: Ut (np x b) -> vb, U2 (b x np) -> v2b
+            SVDB_TRY((launch_panel_public<T, true>(c, rowpanel, np, (int)np, b, Vl, V2l, s1)));
             if (ncl > 0) {
-                size_t cnt = (size_t)b * ncl;
-                scatter_local_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(rowpanel, V, V2, b, np, ncl, k, rk, P,
-                                                                                       a + o * ldl + lb0 * band, ldl, ut_loc, u2_loc);
+                size_t cnt2 = (size_t)b * ncl;
+                scatter_local_kernel<T><<<(unsigned)((cnt2 + 255) / 256), 256, 0, s1>>>(rowpanel, Vl, V2l, b, np, ncl, k, rk, P, A2, ldl,
+                                                                                        ut_loc, u2_loc);
                 c->launches++;
             }
-            if (mr > 0) {
-                T* A3 = a + (o + band) * ldl + lb0 * band;
-                if (ncl > 0) SVDB_TRY(gemm_nn<T>(c, A3, ldl, mr, ncl, band, ut_loc, W));
-                else SVDB_CHECK(c, cudaMemsetAsync(W, 0, mr * band * sizeof(T), s));
-                if (P > 1) SVDB_NCCL(d, nccl().AllReduce(W, W, mr * band, nccl_type<T>(), ncclSum, d->comm, s));
-                if (ncl > 0) SVDB_TRY(rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl));
-            }
+            if (ahead) SVDB_CHECK(c, cudaEventRecord(evL, s1));
         }
+        // s0: the rest of the QR update runs beside the LQ panel
+        if (ncl > 0 && mr > 0) SVDB_TRY(rank_update<T>(c, A2 + band * ldl, ldl, mr, ncl, band, V2 + band * band, W, ncl));
+        if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, evL, 0));
+        if (mr > 0) {
+            T* A3 = a + (o + band) * ldl + lb0 * band;
+            if (ncl > 0) SVDB_TRY(gemm_nn<T>(c, A3, ldl, mr, ncl, band, ut_loc, W));
+            else SVDB_CHECK(c, cudaMemsetAsync(W, 0, mr * band * sizeof(T), s0));
+            if (P > 1) SVDB_NCCL(d, nccl().AllReduce(W, W, mr * band, nccl_type<T>(), ncclSum, d->comm, s0));
+            const bool own_next = (int)((k + 1) % P) == rk && ncl > 0;     // my first b trailing columns are QR panel k+1
+            if (own_next) SVDB_TRY(rank_update<T>(c, A3, ldl, mr, band, band, W, u2_loc, ncl));   // columns of the next QR panel first
+            if (ahead) { SVDB_CHECK(c, cudaEventRecord(evP, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0)); }
+            if (!ahead && ncl > 0) {
+                // single stream: finish the update before the next panel
+                if (own_next) { if (ncl > band) SVDB_TRY(rank_update<T>(c, A3 + band, ldl, mr, ncl - band, band, W, u2_loc + band, ncl)); }
+                else SVDB_TRY(rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl));
+            }
+            SVDB_TRY(qr_panel_and_bcast(k + 1));                           // s1: panel k+1 + broadcast
+            if (ahead && ncl > 0) {
+                if (own_next) { if (ncl > band) SVDB_TRY(rank_update<T>(c, A3 + band, ldl, mr, ncl - band, band, W, u2_loc + band, ncl)); }
+                else SVDB_TRY(rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl));
+            }
+        } else if (k + 1 < nb) {
+            if (ahead) { SVDB_CHECK(c, cudaEventRecord(evP, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0)); }
+            SVDB_TRY(qr_panel_and_bcast(k + 1));
+        }
+    }
+    if (ahead) {   // everything the aux stream did is ordered before the caller's next work on the main stream
+        SVDB_CHECK(c, cudaEventRecord(evQ, s1));
+        SVDB_CHECK(c, cudaStreamWaitEvent(s0, evQ, 0));
     }
     SVDB_CHECK(c, cudaGetLastError());
     return 0;

@@ -315,11 +315,13 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
 
 // panel factorisation for other translation units (the multi-GPU driver in dist.cu)
 template <typename T, bool kTrans>
-int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b) { return launch_panel<T, kTrans>(c, a, lda, m, b, nullptr, nullptr, nullptr); }
-template int launch_panel_public<float, false>(Ctx*, float*, size_t, int, int);
-template int launch_panel_public<float, true>(Ctx*, float*, size_t, int, int);
-template int launch_panel_public<double, false>(Ctx*, double*, size_t, int, int);
-template int launch_panel_public<double, true>(Ctx*, double*, size_t, int, int);
+int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream) {
+    return launch_panel<T, kTrans>(c, a, lda, m, b, V, V2, stream);
+}
+template int launch_panel_public<float, false>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t);
+template int launch_panel_public<float, true>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t);
+template int launch_panel_public<double, false>(Ctx*, double*, size_t, int, int, double*, double*, cudaStream_t);
+template int launch_panel_public<double, true>(Ctx*, double*, size_t, int, int, double*, double*, cudaStream_t);
 
 // Batched panels (uniform shape): one thread-block cluster per matrix, panel resident in the cluster's shared
 // memory, all-reduce over DSMEM.  Used by the small-matrix batched driver (BASELINE configs[4]).
