@@ -151,6 +151,8 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops);
 int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
 /* Debug: per-phase cycle counters of the register panel kernel (all zero unless built with -DSVDB_PANEL_TIMING=1). */
 int svdb200_debug_panel_timing(long long* out16);
+/* same for the stage-2 kernel (-DSVDB_S2_TIMING=1): RIGHT ops of CTA 1 */
+int svdb200_debug_stage2_timing(long long* out16);
 /* Singular values of the bidiagonal (svdb200_bidiag_qr_*, svdb200_svdvals_*): method 0 = automatic (the
  * reference's zero-shift QR sweeps, serial::qrd svd_serial.h:368, for n <= auto_limit, bisection on the
  * Golub-Kahan form above: zero-shift QR needs ~n log(1/tol) sweeps), 1 = always zero-shift QR, 2 = always

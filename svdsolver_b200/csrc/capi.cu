@@ -677,6 +677,7 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
     return probe_peak(c, kind, tflops);
 }
 
+int svdb200_debug_stage2_timing(long long* out16) { return out16 ? stage2_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
 
 int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit) {

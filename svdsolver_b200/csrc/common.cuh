@@ -199,6 +199,7 @@ template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, 
 int probe_peak(Ctx* c, int kind, double* tflops);
 int probe_tc05_tf32(Ctx* c, double* tflops);
 int panel_reg_debug_read(long long* out16);
+int stage2_debug_read(long long* out16);
 int tc05_selftest(Ctx* c, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);
 
 }  // namespace svdb200

@@ -24,6 +24,19 @@ namespace svdb200 {
 
 namespace {
 
+#ifndef SVDB_S2_TIMING
+#define SVDB_S2_TIMING 0
+#endif
+__device__ long long g_s2_dbg[16];
+#define S2_TICK(k)                                                          \
+    do {                                                                    \
+        if (SVDB_S2_TIMING && blockIdx.x == 1 && threadIdx.x == 0) {        \
+            long long _t = clock64();                                       \
+            g_s2_dbg[k] += _t - tick;                                       \
+            tick = _t;                                                      \
+        }                                                                   \
+    } while (0)
+
 // Thread tiling of one window product C = X * Y (nr x L times L x nc): every thread owns a 4 x 2
 // register tile (rows ry + q*RT, columns cx and cx + CT).  Lanes of a warp run along the columns,
 // so Y loads are conflict-free and X loads are broadcasts; odd leading dimensions keep the (at
@@ -163,6 +176,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
     for (int mat = grp; mat < count; mat += ngroups) {
     T* __restrict__ A = A0 + (size_t)mat * N * N;
     int* __restrict__ prog = prog0 + (size_t)mat * N;
+    long long tick = SVDB_S2_TIMING ? clock64() : 0;
+    (void)tick;
     const int rel_tid = nt > 32 ? 32 : 0;                   // the progress counter is published by a thread off thread 0's path
     for (int i = rank; i < n - 1; i += G) {
         int seen = 0;                                         // last observed progress of sweep i-1 (thread 0 only)
@@ -176,10 +191,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
             // ================= RIGHT(p): rows [r0,r2) x cols [r1,r2), window = [F; N] ===================
             {
                 const int q = 2 * p;
+                S2_TICK(0);
                 if (i > 0) {
                     if (tid == 0) seen = wait_progress(&prog[i - 1], q + 4, seen);
+                    S2_TICK(1);
                     __syncthreads();
                 }
+                S2_TICK(2);
                 const int nc = r2 - r1, nr = r2 - r0;
                 const int have = fr;              // rows [0,have) of WR already hold F
                 T nv[kNewPerThread];
@@ -195,7 +213,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                         if (r < nr - have && tx < nc) nv[u] = ld_cg(&A[(size_t)(r0 + have + r) * N + (r1 + tx)]);
                     }
                 }
+                S2_TICK(3);
                 if (tid == 0) reflector_scalars<T>(WR, 1, nc, sc);
+                S2_TICK(4);
                 __syncthreads();
                 build_h<T>(WR, 1, nc, sc, H, ldh, tx, ty, tys);
                 if (have != 0) {
@@ -206,6 +226,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                     }
                 }
                 __syncthreads();
+                S2_TICK(5);
                 // rows [r0,r1) are finished for this sweep; rows [r1,r2) become LEFT(p)'s left block
                 const int keep = r1 - r0;
                 window_product<T>(WR, ldr, H, ldh, nr, nc, nc, (c + 1) / 2, (c + 1) / 2,
@@ -213,7 +234,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                                       if (r < keep) st_cg(&A[(size_t)(r0 + r) * N + (r1 + cc)], v);
                                       else WL[(r - keep) * ldl + cc] = v;
                                   });
+                S2_TICK(6);
                 __syncthreads();
+                S2_TICK(7);
                 if (tid == rel_tid) st_release(&prog[i], q + 1);
             }
             // ================= LEFT(p): rows [r1,r2) x cols [r1,c3), window = [F | N] ====================
@@ -257,6 +280,15 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
     }
     }
 }
+
+}  // namespace
+int stage2_debug_read(long long* out16) {
+    long long z[16] = {};
+    if (cudaMemcpyFromSymbol(out16, g_s2_dbg, sizeof(z)) != cudaSuccess) return 1;
+    cudaMemcpyToSymbol(g_s2_dbg, z, sizeof(z));
+    return 0;
+}
+namespace {
 
 template <typename T>
 __global__ void extract_bidiagonal_kernel(const T* __restrict__ A, int n, T* __restrict__ d, T* __restrict__ e) {

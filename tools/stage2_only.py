@@ -30,3 +30,13 @@ for rep in range(3):
     times.append(e0.elapsed_time(e1))
 ops = sum(2 * ((n - i + b - 1) // b) for i in range(n - 1))
 print(f"stage2 n={n} b={b} {sys.argv[3]}: {min(times):.2f} ms  {[round(t, 2) for t in times]}  ~{min(times) * 1e6 / (4.0 * n):.0f} ns per op on the critical path", flush=True)
+
+import ctypes
+out = (ctypes.c_longlong * 16)()
+capi.lib().svdb200_debug_stage2_timing(out)
+if any(out):
+    tot = sum(out)
+    names = ["LEFT op + loop (everything outside RIGHT)", "poll predecessor", "barrier after poll", "issue N fetch", "reflector scalars (thread 0)",
+             "barrier + build H + store N + barrier", "window product", "barrier after product"]
+    for i, nme in enumerate(names):
+        print(f"  phase {i} {nme:44s} {out[i]:12d} cycles {100.0*out[i]/tot:5.1f}%")
