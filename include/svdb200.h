@@ -149,6 +149,13 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops);
  * the updated block has at least min_elems elements (default), 2: always (tests).  min_elems <= 0
  * keeps the current threshold.  No effect on FP64 handles (tcgen05.mma has no f64 kind). */
 int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
+/* Stage-2 window schedule.  0 (default) = the reference's schedule, bit-for-bit (svd_parallel.h:640-695): its pair count
+ * per sweep is floor((n - j2)/(w-1)) + 1 (the ceil at line 664 acts on an integer quotient), so when that division has a
+ * remainder the last LEFT window leaves a bulge nobody chases and the bidiagonal's singular values drift from those of
+ * the input (1e-3 sigma_1 on stage-1 outputs, up to 1e-1 on generic band matrices).  1 = complete chase:
+ * the same windows and arithmetic, continued until they are empty; orthogonally equivalent to the input (sigma to
+ * round-off).  Use 0 for parity with the reference, 1 when the singular values themselves matter. */
+int svdb200_set_stage2_schedule(svdb200_handle h, int mode);
 /* Debug: per-phase cycle counters of the register panel kernel (all zero unless built with -DSVDB_PANEL_TIMING=1). */
 int svdb200_debug_panel_timing(long long* out16);
 /* same for the stage-2 kernel (-DSVDB_S2_TIMING=1): RIGHT ops of CTA 1 */

@@ -15,6 +15,8 @@ extern "C" {
     /* csc586::parallel::brd_p2<T>  svd_parallel.h:640-695 (band->bidiagonal; d,e optional) */       \
     int svdo_brd_p2_##S(T* A, size_t n, size_t band, T* d, T* e);                                    \
     size_t svdo_brd_p2_schedule_##S(size_t n, size_t band, long long* out, size_t cap);              \
+    /* NOT the reference: same windows and arithmetic, every bulge chased to the end (checker for the complete schedule) */ \
+    int svdo_brd_p2_complete_##S(T* A, size_t n, size_t band, T* d, T* e);                           \
     /* csc586::serial::householder<T>  svd_serial.h:189-216 */                                       \
     int svdo_householder_##S(const T* x, size_t len, T* w, T* H, T* tau);                            \
     /* parallel::qr / lq  svd_parallel.h:133-226; qr_apply / lq_apply 243-281 */                      \

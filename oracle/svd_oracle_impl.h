@@ -439,6 +439,67 @@ int FN(svdo_brd_p2)(T* A, size_t n, size_t band, T* d, T* e) {
     return 0;
 }
 
+/* Window ops of the complete variant: identical to win_right / win_left except that a zero vector (sum of squares == 0,
+ * which the extra windows at the matrix edge can meet, and which makes the reference formula divide by zero) is left
+ * alone: alpha = tau = 0, i.e. H = I built and applied with the same operations. */
+static void FN(win_right_g)(T* A, size_t n, size_t i1, size_t i2, size_t j1, size_t j2, T* w, T* H, T* tmp) {
+    size_t nr = i2 - i1, nc = j2 - j1;
+    T tau, acc = 0;
+    for (size_t i = 0; i < nc; ++i) acc = acc + A[i1 * n + j1 + i] * A[i1 * n + j1 + i];
+    if (acc == 0) { for (size_t i = 0; i < nc; ++i) w[i] = A[i1 * n + j1 + i] * (T)0; w[0] = (T)1.; tau = (T)0; }
+    else FN(householder)(A + i1 * n + j1, 1, nc, w, &tau);
+    FN(hh_transform)(w, nc, tau, H);
+    FN(mm)(tmp, nc, A + i1 * n + j1, n, H, nc, nr, nc, nc);
+    for (size_t r = 0; r < nr; ++r) memcpy(A + (i1 + r) * n + j1, tmp + r * nc, sizeof(T) * nc);
+}
+static void FN(win_left_g)(T* A, size_t n, size_t i1, size_t i2, size_t j1, size_t j2, T* w, T* H, T* tmp) {
+    size_t nr = i2 - i1, nc = j2 - j1;
+    T tau, acc = 0;
+    for (size_t i = 0; i < nr; ++i) acc = acc + A[(i1 + i) * n + j1] * A[(i1 + i) * n + j1];
+    if (acc == 0) { for (size_t i = 0; i < nr; ++i) w[i] = A[(i1 + i) * n + j1] * (T)0; w[0] = (T)1.; tau = (T)0; }
+    else FN(householder)(A + i1 * n + j1, n, nr, w, &tau);
+    FN(hh_transform)(w, nr, tau, H);
+    FN(mm)(tmp, nc, H, nr, A + i1 * n + j1, n, nr, nr, nc);
+    for (size_t r = 0; r < nr; ++r) memcpy(A + (i1 + r) * n + j1, tmp + r * nc, sizeof(T) * nc);
+}
+
+/* Stage 2 with a COMPLETE chase (not the reference's schedule): svd_parallel.h:664 computes the number of window pairs
+ * of a sweep with an integer division inside ceil(), i.e. floor; when (n - t_left.j2) is not a multiple of w-1 the last
+ * LEFT window leaves a bulge that no RIGHT window chases and the result is no longer orthogonally equivalent to the
+ * input.  This variant keeps emitting window pairs until both are empty -- same windows otherwise, same
+ * arithmetic -- and is the checker for the product's optional complete schedule (svdb200_set_stage2_schedule). */
+int FN(svdo_brd_p2_complete)(T* A, size_t n, size_t band, T* d, T* e) {
+    if (n < 2) return -1;
+    size_t m = n, w_ = band + 1;
+    T* w = (T*)malloc(sizeof(T) * (2 * w_ + 4 * w_ * w_ + 4 * w_ * w_));
+    T* H = w + 2 * w_;
+    T* tmp = H + 4 * w_ * w_;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        size_t end_i = SVDO_MIN(i + w_, m), end_j = SVDO_MIN(i + w_, n);
+        size_t li1 = i, li2 = end_i, lj1 = i + 1, lj2 = end_j;
+        FN(win_right_g)(A, n, li1, li2, lj1, lj2, w, H, tmp);
+        lj2 = SVDO_MIN(i + w_ + w_ - 1, n);
+        li1 = li1 + 1; lj1 = i + 1;
+        FN(win_left_g)(A, n, li1, li2, lj1, lj2, w, H, tmp);
+        if (w_ < 2) continue;
+        for (;;) {
+            size_t ei = SVDO_MIN(li2 + w_ - 1, m);
+            size_t sj = SVDO_MIN(lj1 + w_ - 1, n);
+            size_t ej3 = SVDO_MIN(lj2 + w_ - 1, n);
+            size_t ri1 = li1, ri2 = ei, rj1 = sj, rj2 = lj2;
+            int did = 0;
+            li1 = li2; li2 = ei; lj1 = sj; lj2 = ej3;
+            if (rj2 > rj1 && ri2 > ri1) { FN(win_right_g)(A, n, ri1, ri2, rj1, rj2, w, H, tmp); did = 1; }
+            if (lj2 > lj1 && li2 > li1) { FN(win_left_g)(A, n, li1, li2, lj1, lj2, w, H, tmp); did = 1; }
+            if (!did) break;
+        }
+    }
+    if (d) for (size_t i = 0; i < n; ++i) d[i] = A[i * n + i];
+    if (e) for (size_t i = 0; i + 1 < n; ++i) e[i] = A[i * n + i + 1];
+    free(w);
+    return 0;
+}
+
 /* Window schedule only (no arithmetic): fills out[] with 6-tuples {kind(0=right,1=left),i1,i2,j1,j2,sweep}.
  * Returns the number of windows; out may be NULL to count.  Used to pin the closed form in the
  * CUDA kernel (SURVEY 8a'') against the reference recurrence. */

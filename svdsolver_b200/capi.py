@@ -217,6 +217,10 @@ class Handle:
         """FP32 tcgen05/TMEM/TMA trailing update: 0 off, 1 auto (size threshold), 2 always."""
         self._check(lib().svdb200_set_tc05(self.h, ctypes.c_int(mode), ctypes.c_longlong(min_elems)))
 
+    def set_stage2_schedule(self, mode):
+        """0 = the reference's window schedule (default, parity); 1 = complete chase (singular values preserved)."""
+        self._check(lib().svdb200_set_stage2_schedule(self.h, ctypes.c_int(mode)))
+
     def set_qr_method(self, method, auto_limit=0):
         """0 auto, 1 zero-shift QR sweeps (reference algorithm), 2 bisection."""
         self._check(lib().svdb200_set_qr_method(self.h, ctypes.c_int(method), Z(auto_limit)))

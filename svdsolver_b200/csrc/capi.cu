@@ -680,6 +680,14 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
 int svdb200_debug_stage2_timing(long long* out16) { return out16 ? stage2_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
 
+int svdb200_set_stage2_schedule(svdb200_handle h, int mode) {
+    if (!h || mode < 0 || mode > 1) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->stage2_complete = mode;
+    for (auto* s : c->pool) if (s) s->stage2_complete = mode;
+    return 0;
+}
+
 int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit) {
     if (!h || method < 0 || method > 2) return SVDB200_E_ARG;
     Ctx* c = reinterpret_cast<Ctx*>(h);

@@ -65,6 +65,7 @@ struct Ctx {
     int use_tc05 = 1;                       // 0 off, 1 when the update is large enough, 2 always (tests)
     long long tc05_min_elems = 8LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
     // singular values of the bidiagonal: 0 auto (zero-shift QR up to qr_auto_limit, bisection above), 1 QR, 2 bisection
+    int stage2_complete = 0;                // 0: the reference's window schedule (parity), 1: complete chase
     int qr_method = 0;
     size_t qr_auto_limit = 1024;
     void* bis_ws = nullptr;

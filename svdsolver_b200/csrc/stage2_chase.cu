@@ -63,8 +63,9 @@ __device__ __forceinline__ int wait_progress(const int* p, int need, int seen) {
 }
 
 // Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.
+// guard (complete schedule only): a zero vector keeps alpha = tau = 0, i.e. H = I, instead of dividing by zero
 template <typename T>
-__device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* sc) {
+__device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* sc, bool guard) {
     T acc = (T)0;
     int i = 0;
     for (; i + 8 <= L; i += 8) {               // the loads are independent: let them pipeline
@@ -79,7 +80,8 @@ __device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* 
         acc = RN<T>::add(acc, RN<T>::mul(v, v));
     }
     T alpha, tau;
-    householder_scalars<T>(x[0], RN<T>::sqrt(acc), alpha, tau);
+    if (guard && acc == (T)0) { alpha = (T)0; tau = (T)0; }
+    else householder_scalars<T>(x[0], RN<T>::sqrt(acc), alpha, tau);
     sc[0] = alpha;
     sc[1] = tau;
 }
@@ -156,7 +158,7 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
 
 template <typename T, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T* __restrict__ A0, int n, int band, int* __restrict__ prog0,
-                                                                      int count, int G) {
+                                                                      int count, int G, int complete) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = band, w = band + 1;
     const int ldr = c + 1, ldl = 2 * c + 1, ldh = c + 1;
@@ -182,7 +184,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
     for (int i = rank; i < n - 1; i += G) {
         int seen = 0;                                         // last observed progress of sweep i-1 (thread 0 only)
         const int top_j2 = min(i + 2 * w - 1, n);
-        const int npairs = 1 + (n - top_j2) / c + 1;
+        // reference schedule: svd_parallel.h:664 (floor, the ceil there acts on an integer quotient).  complete: pairs
+        // while their window is non-empty -- chases every bulge to the matrix edge (see svdb200_set_stage2_schedule).
+        const int npairs = complete ? (n - i - 1 + c - 1) / c : 1 + (n - top_j2) / c + 1;
         int fr = 0;                               // rows of the forwarded block sitting in WR (0: none)
         for (int p = 0; p < npairs; ++p) {
             const int r0 = (p == 0) ? i : min(i + 1 + (p - 1) * c, n);
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                     }
                 }
                 S2_TICK(3);
-                if (tid == 0) reflector_scalars<T>(WR, 1, nc, sc);
+                if (tid == 0) reflector_scalars<T>(WR, 1, nc, sc, complete != 0);
                 S2_TICK(4);
                 __syncthreads();
                 build_h<T>(WR, 1, nc, sc, H, ldh, tx, ty, tys);
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                     int r = ty + u * tys;
                     if (r < nr && tx < nn) nv[u] = ld_cg(&A[(size_t)(r1 + r) * N + (r2 + tx)]);
                 }
-                if (tid == 0) reflector_scalars<T>(WL, ldl, nr, sc);
+                if (tid == 0) reflector_scalars<T>(WL, ldl, nr, sc, complete != 0);
                 __syncthreads();
                 build_h<T>(WL, ldl, nr, sc, H, ldh, tx, ty, tys);
 #pragma unroll
@@ -344,8 +348,8 @@ int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int co
         prog = c->batch_prog;
     }
     SVDB_CHECK(c, cudaMemsetAsync(prog, 0, sizeof(int) * n * (size_t)count, c->stream));
-    int ni = (int)n, bi = cb, cnt = count, gi = (int)G;
-    void* args[] = {&a, &ni, &bi, &prog, &cnt, &gi};
+    int ni = (int)n, bi = cb, cnt = count, gi = (int)G, complete = c->stage2_complete;
+    void* args[] = {&a, &ni, &bi, &prog, &cnt, &gi, &complete};
     SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(nt), args, smem, c->stream));
     c->launches++;
     if (d || e) {

@@ -56,6 +56,16 @@ class Oracle:
         assert rc == 0
         return x, d, e
 
+    def brd_p2_complete(self, a, band):
+        """NOT the reference: same windows / arithmetic with every bulge chased to the end."""
+        x = np.ascontiguousarray(a).copy()
+        n = x.shape[0]
+        d = np.zeros(n, x.dtype)
+        e = np.zeros(n - 1, x.dtype)
+        rc = getattr(self.lib, "svdo_brd_p2_complete_" + self.suf(x))(self.ptr(x), ctypes.c_size_t(n), ctypes.c_size_t(band), self.ptr(d), self.ptr(e))
+        assert rc == 0
+        return x, d, e
+
     def qrd(self, d, e):
         d = np.ascontiguousarray(d).copy()
         e = np.ascontiguousarray(e).copy()

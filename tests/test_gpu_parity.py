@@ -383,3 +383,37 @@ def test_stage1_tall_panels_invariants(capi, suf, n, b):
     s0 = torch.linalg.svdvals(torch.from_numpy(a.astype(np.float64)).cuda()).cpu().numpy()   # test-only reference (cuSOLVER)
     s1 = torch.linalg.svdvals(torch.from_numpy(band).cuda()).cpu().numpy()
     assert np.abs(s0 - s1).max() <= tol * s0[0]
+
+
+# ------------------------------------------------------------------ complete stage-2 schedule (option) -----------------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n,b", [(64, 4), (65, 4), (100, 7), (96, 32), (256, 32), (130, 16), (512, 64)])
+def test_stage2_complete_schedule_bit_exact_vs_oracle_and_sigma(capi, oracle, suf, n, b):
+    """svdb200_set_stage2_schedule(1): same windows and arithmetic as the reference, every bulge chased to the end.
+    Bit-exact against the oracle's complete-chase variant; singular values of the band are preserved."""
+    rng = np.random.default_rng(n * 7 + b)
+    band = np.triu(np.tril(rng.random((n, n)) * 5, b)).astype(DT[suf])
+    ref, dr, er = oracle.brd_p2_complete(band, b)
+    with handle(capi, n, b, suf) as h:
+        h.set_stage2_schedule(1)
+        out, d, e = h.band_to_bidiag(band, b)
+    assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
+    s0 = np.linalg.svd(band.astype(np.float64), compute_uv=False)
+    s1 = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+    assert np.abs(s1 - s0).max() <= (2e-5 if suf == "f32" else 1e-13) * s0[0]
+
+
+@pytest.mark.parametrize("suf,n,b", [("f64", 1024, 32), ("f32", 768, 64), ("f64", 2048, 64)])
+def test_svdvals_complete_schedule_matches_lapack(capi, suf, n, b):
+    """full chain with the complete schedule: sigma == LAPACK sigma of the INPUT matrix (the reference schedule is off by
+    ~1e-3 sigma_1 here); also through the batched path"""
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    s0 = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+    with handle(capi, n, b, suf) as h:
+        h.set_stage2_schedule(1)
+        sig, _ = h.svdvals(a.copy(), b)
+        sigb = h.svdvals_batched(np.stack([a, a]), b) if n <= 1024 else None
+    tol = 2e-5 if suf == "f32" else 1e-11
+    assert np.abs(sig.astype(np.float64) - s0).max() <= tol * s0[0]
+    if sigb is not None:
+        assert np.abs(sigb[1].astype(np.float64) - s0).max() <= tol * s0[0]

@@ -184,3 +184,48 @@ def test_stage2_cross_sweep_dependency_lag(n, b):
                 if overlap(oa, ob):
                     worst = max(worst, qa - q)
     assert worst <= 3
+
+
+@pytest.mark.parametrize("n,b", [(64, 4), (65, 4), (100, 7), (96, 32), (256, 32), (130, 16)])
+def test_complete_chase_preserves_singular_values(oracle, n, b):
+    """The reference's stage-2 schedule is not orthogonally equivalent to its input; the complete-chase
+    variant of the oracle (checker of svdb200_set_stage2_schedule(1)) is: sigma(bidiagonal) == sigma(band)."""
+    rng = np.random.default_rng(n + b)
+    band = np.triu(np.tril(rng.random((n, n)) * 5, b))
+    s0 = np.linalg.svd(band, compute_uv=False)
+    _, d, e = oracle.brd_p2_complete(band, b)
+    s1 = np.linalg.svd(np.diag(d) + np.diag(e, 1), compute_uv=False)
+    assert np.abs(s1 - s0).max() <= 1e-13 * s0[0]
+    _, dr, er = oracle.brd_p2(band, b)
+    sr = np.linalg.svd(np.diag(dr) + np.diag(er, 1), compute_uv=False)
+    assert np.abs(sr - s0).max() > 1e-6 * s0[0]      # the flaw this option exists for
+
+
+@pytest.mark.parametrize("n,b", [(64, 4), (65, 4), (100, 7), (96, 32), (40, 4), (33, 32)])
+def test_complete_schedule_dependency_lag(n, b):
+    """the q+4 pipelining rule of the kernel also holds for the complete schedule (brute force over all window pairs)"""
+    c, w = b, b + 1
+
+    def ops(i):
+        out = [(i, min(i + w, n), i + 1, min(i + w, n)), (i + 1, min(i + w, n), i + 1, min(i + 2 * w - 1, n))]
+        k = 0
+        while True:
+            r0, r1, r2, c3 = (min(i + 1 + (k + j) * c, n) for j in range(4))
+            if not r2 > r1:
+                break
+            out.append((r0, r2, r1, r2))
+            out.append((r1, r2, r1, c3) if c3 > r1 else None)
+            k += 1
+        return out
+
+    def overlap(a, bb):
+        return a and bb and a[0] < bb[1] and bb[0] < a[1] and a[2] < bb[3] and bb[2] < a[3]
+
+    worst = 0
+    for i in range(n - 2):
+        A, B = ops(i), ops(i + 1)
+        for q, ob in enumerate(B):
+            for qa, oa in enumerate(A):
+                if overlap(oa, ob):
+                    worst = max(worst, qa - q)
+    assert worst <= 3

@@ -22,6 +22,7 @@ def flops(n):
 def c3(n=16384, band=64, dt=np.float64):
     tdt = torch.float64 if dt == np.float64 else torch.float32
     h = capi.Handle(n, band, dt)
+    h.set_stage2_schedule(int(os.environ.get("S2_COMPLETE", "0")))
     s = torch.cuda.Stream()
     h.set_stream(s.cuda_stream)
     a = torch.empty(n, n, device="cuda", dtype=tdt)
