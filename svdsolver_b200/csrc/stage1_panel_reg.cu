@@ -65,12 +65,53 @@ template <> struct LLWord<double> {
     }
 };
 
+// The same words in shared memory: a CTA pushes them into a PEER's shared memory (st.shared::cluster on the mapa
+// address) and the peer polls its own copy -- the per-column all-reduce inside a cluster needs no barrier.cluster.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_to_rank(unsigned local_addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+template <typename T> struct LLSmem;
+template <> struct LLSmem<float> {
+    static __device__ __forceinline__ void push(unsigned remote, float v, unsigned seq) {
+        asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(remote), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+    }
+    static __device__ __forceinline__ bool try_load(unsigned local, unsigned seq, float& v) {
+        unsigned a, b;
+        asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(local) : "memory");
+        v = __uint_as_float(a);
+        return b == seq;
+    }
+};
+template <> struct LLSmem<double> {
+    static __device__ __forceinline__ void push(unsigned remote, double v, unsigned seq) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"((unsigned)u), "r"(seq), "r"((unsigned)(u >> 32)), "r"(seq) : "memory");
+    }
+    static __device__ __forceinline__ bool try_load(unsigned local, unsigned seq, double& v) {
+        unsigned a, b, c2, d;
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "r"(local) : "memory");
+        v = __longlong_as_double((long long)(((unsigned long long)c2 << 32) | a));
+        return b == seq && d == seq;
+    }
+};
+
 template <typename T, int CPL>
 __device__ __forceinline__ T pick(const T (&v)[CPL], int u) {
     T r = v[0];
 #pragma unroll
     for (int q = 1; q < CPL; ++q) r = (u == q) ? v[q] : r;
     return r;
+}
+
+// elements of the staging area: max(ROWS x (b+1), the l1 word buffers: 2 parities x (CS + 1) vectors x b entries x 16 B)
+template <typename T>
+__host__ __device__ inline size_t stage_elems(int rows, int b, int max_cs) {
+    const size_t ps = (size_t)rows * (b + 1);
+    const size_t l1 = ((size_t)2 * (max_cs + 1) * b * 16 + sizeof(T) - 1) / sizeof(T) + 4;
+    return ps > l1 ? ps : l1;
 }
 
 template <typename T, bool kTrans, bool kCluster, int RPT, int CPL>
@@ -90,8 +131,11 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     const int R = max(0, min(ROWS, m - r0));
     const int ld = b + 1, slot = 2 * b;
     T* lred = reinterpret_cast<T*>(smem_raw);            // 2 * slot
-    T* Ps = lred + 2 * slot;                             // ROWS x ld (transposed staging + epilogue)
-    T* Gm = Ps + (size_t)ROWS * ld;                      // b x b
+    T* Ps = lred + 2 * slot;                             // ROWS x ld (transposed staging + epilogue); during the column
+                                                         // loop the same bytes hold the pushed all-reduce words (l1)
+    constexpr int kMaxCS = 16;
+    const size_t ps_elems = stage_elems<T>(ROWS, b, kMaxCS);
+    T* Gm = Ps + ps_elems;                               // b x b
     T* zs = Gm + b * b;                                  // b
     T* piv = zs + b;                                     // b
     T* taus = piv + b;                                   // b
@@ -125,6 +169,14 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         }
     }
     for (int e = tid; e < b * b; e += nt) Gm[e] = (T)0;
+    // l1: pushed all-reduce words, [parity][sender rank 0..CS-1, CS = pivot row][column] x 16 B, aliasing Ps
+    const unsigned l1_base = (smem_addr(Ps) + 15u) & ~15u;
+    if (kCluster) {
+        __syncthreads();                                  // the transposed load above is done with Ps
+        unsigned* z = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(Ps) + (l1_base - smem_addr(Ps)));
+        for (int e = tid; e < 2 * (kMaxCS + 1) * b * 4; e += nt) z[e] = 0u;
+        cg::this_cluster().sync();                        // every peer's buffers are cleared before the first push
+    }
 
     const int kmax = min(b, m);
     // dots of column 0 (rows > 0) with every column
@@ -172,22 +224,59 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             for (int q = 1; q < kWarps; ++q) s += psum[q * b + c];
             if (kCluster) mine[c] = s; else st_cg(&mine[c], s);
         }
-        if (kCluster) cg::this_cluster().sync(); else grid_barrier(bar, (unsigned)G, gen);
+        if (kCluster) __syncthreads(); else grid_barrier(bar, (unsigned)G, gen);
         PANEL_TICK(2);
         // ---- all-reduce across CTAs in a fixed association -------------------------------------------------
         {
             const int jowner = j / ROWS;                 // CTA that holds global row j
             if (kCluster) {
-                // level 1: the CS partial vectors of this cluster, read over DSMEM
+                // level 1 (inside the cluster), push model: every CTA writes its b partial sums -- and the owner of
+                // row j the pivot row -- as flag-stamped words into the shared memory of all CS peers (itself included),
+                // then polls its OWN shared memory until the CS + 1 vectors of this column have arrived.  No
+                // barrier.cluster, one one-way DSMEM latency.  Parity double buffering is safe: a peer can push column
+                // j + 2 only after it has received my column j + 1, which I send after I am done with column j.
+                const unsigned seq1 = epoch * 128u + (unsigned)(j + 1);
+                const unsigned par_off = (unsigned)(j & 1) * (unsigned)((kMaxCS + 1) * b * 16);
+                const bool own_cta = (jowner == g);
+                if (in2d) {
+                    const int c = tx;
+                    const T sv = mine[c];
+                    const T pvv = own_cta ? pivslot[c] : (T)0;
+                    for (int q = tyy; q < CS; q += rgroups) {
+                        const unsigned rbase = map_to_rank(l1_base + par_off, (unsigned)q);
+                        LLSmem<T>::push(rbase + (unsigned)((crank * b + c) * 16), sv, seq1);
+                        if (own_cta) LLSmem<T>::push(rbase + (unsigned)((kMaxCS * b + c) * 16), pvv, seq1);
+                    }
+                }
                 const int chunk = (CS + rgroups - 1) / rgroups;
                 if (in2d) {
                     const int c = tx, part = tyy;
                     const int q0 = part * chunk, q1 = min(CS, q0 + chunk);
                     T s = (T)0;
-                    cg::cluster_group clg = cg::this_cluster();
-#pragma unroll 4
-                    for (int q = q0; q < q1; ++q) s += clg.map_shared_rank(lred, q)[(j & 1) * slot + c];
-                    if (part == 0 && jowner / CS == cl) piv[c] = clg.map_shared_rank(lred, jowner - cl * CS)[(j & 1) * slot + b + c];
+                    unsigned polls = 0;
+                    unsigned long long t0 = 0;
+                    for (int q = q0; q < q1; ++q) {
+                        T v;
+                        while (!LLSmem<T>::try_load(l1_base + par_off + (unsigned)((q * b + c) * 16), seq1, v)) {
+                            if ((++polls & 0xffffu) == 0u) {
+                                unsigned long long now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ull) __trap();
+                            }
+                        }
+                        s += v;
+                    }
+                    if (part == 0 && jowner / CS == cl) {
+                        T v;
+                        while (!LLSmem<T>::try_load(l1_base + par_off + (unsigned)((kMaxCS * b + c) * 16), seq1, v)) {
+                            if ((++polls & 0xffffu) == 0u) {
+                                unsigned long long now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ull) __trap();
+                            }
+                        }
+                        piv[c] = v;
+                    }
                     psum[part * b + c] = s;
                 }
                 __syncthreads();
@@ -276,7 +365,6 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 if (valid[u] && cu[u] < j) Gm[cu[u] * b + j] = piv[cu[u]] + alpha * zs[cu[u]];
             if (lane == 0) taus[j] = tau;
         }
-        if (sizeof(T) == 8) {
         // ---- fused pass: rank-1 update of column j, dots for column j+1 ---------------------------------------
         // Branch-free: per-lane column predicates become factors (fm = 0 for finished columns), per-row predicates
         // become a zero reflector entry, so every (row, column) is one FMA for the update, one select for the
@@ -306,34 +394,6 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
 #pragma unroll
                 for (int u = 0; u < CPL; ++u) acc[u] += a[i][u] * pe;
             }
-        }
-        } else {
-        // ---- fused pass: rank-1 update of column j, dots for column j+1 ---------------------------------------
-        const int lj = j & 31, uj = j >> 5, ln = (j + 1) & 31, un = (j + 1) >> 5;
-        const bool more = (j + 1 < kmax);
-#pragma unroll
-        for (int u = 0; u < CPL; ++u) acc[u] = (T)0;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int rl = w + kWarps * i;
-            const int grow = r0 + rl;
-            const T xj = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i], uj), lj);
-            if (rl < R && grow >= j) {
-                const T wv = (grow == j) ? (T)1 : xj * alpha;
-#pragma unroll
-                for (int u = 0; u < CPL; ++u) {
-                    if (cu[u] > j) a[i][u] -= wv * fsr[u];
-                    else if (cu[u] == j) a[i][u] = (grow == j) ? beta : wv;
-                }
-            }
-            if (more) {
-                const T pn = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i], un), ln);
-                if (rl < R && grow > j + 1) {
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) acc[u] += a[i][u] * pn;
-                }
-            }
-        }
         }
         // psum / zs / piv are rewritten only after the next __syncthreads-protected phases
         __syncthreads();
@@ -392,7 +452,8 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
 }
 
 inline size_t reg_smem_bytes(int rows, int b, size_t esz) {
-    return ((size_t)4 * b + (size_t)rows * (b + 1) + (size_t)b * b + 3 * (size_t)b + (size_t)kWarps * b + kThreads + 8) * esz;
+    const size_t stage = esz == 8 ? stage_elems<double>(rows, b, 16) : stage_elems<float>(rows, b, 16);
+    return ((size_t)4 * b + stage + (size_t)b * b + 3 * (size_t)b + (size_t)kWarps * b + kThreads + 8) * esz;
 }
 
 template <typename T, bool kTrans, int RPT, int CPL>
