@@ -29,7 +29,7 @@ struct Ctx {
     cudaEvent_t lev[4] = {};
     int lookahead = 1;
     int panel_reg = 1;             // use the register-resident panel kernel when the shape allows
-    int panel_reg_min = 16 * 256;  // ... for panels taller than this (SVDB200_PANEL_REG_MIN)
+    int panel_reg_min = 768;       // ... for panels taller than this (SVDB200_PANEL_REG_MIN); below, the shared-memory kernel
     void* w = nullptr;             // band * max_n  : W = V^T A  /  max_n * band : W = A U^T
     void* wpart = nullptr;         // split-K partials
     size_t wpart_elems = 0;

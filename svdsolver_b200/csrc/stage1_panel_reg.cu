@@ -115,7 +115,7 @@ __host__ __device__ inline size_t stage_elems(int rows, int b, int max_cs) {
 }
 
 template <typename T, bool kTrans, bool kCluster, int RPT, int CPL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1)
 panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, T* __restrict__ red,
                  unsigned* __restrict__ bar, int NC, unsigned epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -375,6 +375,49 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         bool isj[CPL];
 #pragma unroll
         for (int u = 0; u < CPL; ++u) { fm[u] = (cu[u] > j) ? fsr[u] : (T)0; isj[u] = (cu[u] == j); acc[u] = (T)0; }
+        // The two broadcasts per row (pivot column before the update, next pivot column after it) are issued for ALL
+        // rows of the slice before their results are consumed: a shuffle has ~30 cycles of latency and with two warps
+        // per scheduler a row-by-row order leaves the pass waiting on it (short-scoreboard stalls, prof_r1_panel4).
+        // (float only: in double the batched form does not fit the 128 registers that two CTAs per SM allow)
+        if constexpr (sizeof(T) == 4) {
+        constexpr int CH = RPT;
+        T bc[CH];
+#pragma unroll
+        for (int i0 = 0; i0 < RPT; i0 += CH) {
+#pragma unroll
+            for (int ii = 0; ii < CH; ++ii) bc[ii] = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i0 + ii], uj), lj);
+#pragma unroll
+            for (int ii = 0; ii < CH; ++ii) {
+                const int i = i0 + ii;
+                const int rl = w + kWarps * i;
+                const int grow = r0 + rl;
+                const bool act = (rl < R) && (grow >= j);
+                const T wv = act ? ((grow == j) ? (T)1 : bc[ii] * alpha) : (T)0;
+                const T cj = (grow == j) ? beta : wv;
+#pragma unroll
+                for (int u = 0; u < CPL; ++u) {
+                    const T nv = a[i][u] - wv * fm[u];
+                    a[i][u] = (isj[u] && act) ? cj : nv;
+                }
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int i0 = 0; i0 < RPT; i0 += CH) {
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii) bc[ii] = __shfl_sync(0xffffffffu, pick<T, CPL>(a[i0 + ii], un), ln);
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii) {
+                    const int i = i0 + ii;
+                    const int rl = w + kWarps * i;
+                    const int grow = r0 + rl;
+                    const T pe = ((rl < R) && (grow > j + 1)) ? bc[ii] : (T)0;
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) acc[u] += a[i][u] * pe;
+                }
+            }
+        }
+        } else {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int rl = w + kWarps * i;
@@ -394,6 +437,7 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
 #pragma unroll
                 for (int u = 0; u < CPL; ++u) acc[u] += a[i][u] * pe;
             }
+        }
         }
         // psum / zs / piv are rewritten only after the next __syncthreads-protected phases
         __syncthreads();
