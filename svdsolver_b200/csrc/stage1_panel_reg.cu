@@ -378,9 +378,9 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         // The two broadcasts per row (pivot column before the update, next pivot column after it) are issued for ALL
         // rows of the slice before their results are consumed: a shuffle has ~30 cycles of latency and with two warps
         // per scheduler a row-by-row order leaves the pass waiting on it (short-scoreboard stalls, prof_r1_panel4).
-        // (float only: in double the batched form does not fit the 128 registers that two CTAs per SM allow)
-        if constexpr (sizeof(T) == 4) {
-        constexpr int CH = RPT;
+        // (double: chunks of 8 rows; it runs one CTA per SM with the full register file)
+        if constexpr (true) {
+        constexpr int CH = sizeof(T) == 8 ? (RPT < 8 ? RPT : 8) : RPT;
         T bc[CH];
 #pragma unroll
         for (int i0 = 0; i0 < RPT; i0 += CH) {
