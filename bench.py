@@ -55,7 +55,7 @@ def workload_config(extra=None):
     cfg = {
         "workload": "reference sweep n=320..3840 step 320, band 32, float and double, dense->band->bidiagonal "
                     "(BASELINE configs[1]); 24 matrices per step",
-        "band": BAND, "sizes": SIZES, "dtypes": ["f64", "f32"], "stage1_order": "panel",
+        "band": BAND, "sizes": SIZES, "dtypes": ["f64", "f32"], "stage1_order": "panel", "pipelining": "per dtype the 12 matrices go through svdb200_bidiagonalize_many_*: stage 2 of matrix i overlaps stage 1 of matrix i+1",
         "inputs": "U[0,5) splitmix64 stream, seed 586+n", "l2": "fresh 0.8 GB input copy set per step (> 126 MB L2)",
     }
     if extra:
@@ -339,9 +339,16 @@ def main():
         for n, suf, a in cur:
             handles[suf].fill_uniform_dev(a.data_ptr(), n * n, 586 + n, 0.0, 5.0)
 
+    # one call per dtype hands the 12 matrices of the sweep to svdb200_bidiagonalize_many_dev_*: stage 2 of matrix i runs
+    # beside stage 1 of matrix i+1 (results identical to one call per matrix; tests/test_gpu_parity.py)
+    dmany = {suf: [torch.empty(n, device=dev, dtype=tdt[suf]) for n in sizes] for suf, _ in DTYPES}
+    emany = {suf: [torch.empty(n, device=dev, dtype=tdt[suf]) for n in sizes] for suf, _ in DTYPES}
+
     def step(cur):
-        for n, suf, a in cur:
-            handles[suf].bidiagonalize_dev(a.data_ptr(), n, BAND, dbuf[suf].data_ptr(), ebuf[suf].data_ptr())
+        for suf, _ in DTYPES:
+            mats = [(n, a) for n, s_, a in cur if s_ == suf]
+            handles[suf].bidiagonalize_many_dev([a.data_ptr() for _, a in mats], [n for n, _ in mats], BAND,
+                                                [x.data_ptr() for x in dmany[suf]], [x.data_ptr() for x in emany[suf]])
 
     def barrier():
         if world > 1:
@@ -483,8 +490,10 @@ def main():
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
-        for n, suf, _, buf, dh, eh in host:
-            handles[suf].bidiagonalize_inplace(buf.data_ptr(), n, BAND, dh.data_ptr(), eh.data_ptr())
+        for suf, _ in DTYPES:
+            hs = [x for x in host if x[1] == suf]
+            handles[suf].bidiagonalize_many_inplace([x[3].data_ptr() for x in hs], [x[0] for x in hs], BAND,
+                                                    [x[4].data_ptr() for x in hs], [x[5].data_ptr() for x in hs])
         a1.record(stream)
         torch.cuda.synchronize()
         if s > 0:
@@ -494,7 +503,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms = float(t.item())
     e2e = {"value": world * step_flops * e2e_steps / (tot_ms * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "svdb200_bidiagonalize_{f64,f32} (host pointers, pinned)"}
+           "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "svdb200_bidiagonalize_many_{f64,f32} (host pointers, pinned; double-buffered copies)"}
 
     # ---- multi-GPU stage 1 (BASELINE config 4 shape): 1-D block-cyclic columns, NCCL panel broadcast ----
     dist_out = None

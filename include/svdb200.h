@@ -103,6 +103,17 @@ int svdb200_bidiagonalize_f64(svdb200_handle h, double* a, size_t m, size_t n, s
 int svdb200_bidiagonalize_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, int order, float* d_dev, float* e_dev);
 int svdb200_bidiagonalize_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, int order, double* d_dev, double* e_dev);
 
+/* The same for a LIST of independent matrices (sizes may differ; every n[i] <= max_n and band | n[i]): stage 2 of matrix i
+ * runs on its own stream beside stage 1 of matrix i+1 (both are latency-bound at moderate n), and in the host-pointer
+ * variant the H2D / D2H copies are double-buffered behind the kernels.  a, d, e are host arrays of `count` pointers
+ * (device pointers for _dev, host pointers otherwise; d / e or single entries may be NULL).  Results are identical to
+ * `count` calls of svdb200_bidiagonalize_*; this is what a benchmark loop over instances (timing.h:55-91) becomes when
+ * the instances are handed over together. */
+int svdb200_bidiagonalize_many_f32(svdb200_handle h, size_t count, float* const* a, const size_t* n, size_t band, int order, float* const* d, float* const* e);
+int svdb200_bidiagonalize_many_f64(svdb200_handle h, size_t count, double* const* a, const size_t* n, size_t band, int order, double* const* d, double* const* e);
+int svdb200_bidiagonalize_many_dev_f32(svdb200_handle h, size_t count, float* const* a_dev, const size_t* n, size_t band, int order, float* const* d_dev, float* const* e_dev);
+int svdb200_bidiagonalize_many_dev_f64(svdb200_handle h, size_t count, double* const* a_dev, const size_t* n, size_t band, int order, double* const* d_dev, double* const* e_dev);
+
 /* ---- Fused chain: singular values of a dense matrix ------------------------------
  * dense -> brd_p1 -> brd_p2 -> qrd.  `a` is overwritten by the bidiagonalised matrix. */
 int svdb200_svdvals_f32(svdb200_handle h, float* a, size_t m, size_t n, size_t band, int order, float* sigma);

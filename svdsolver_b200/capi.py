@@ -141,6 +141,24 @@ class Handle:
     def bidiagonalize_dev(self, a_ptr, n, band, d_ptr, e_ptr, order=ORDER_PANEL):
         self._check(self._fn("bidiagonalize_dev")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order), _p(d_ptr), _p(e_ptr)))
 
+    def _ptr_arrays(self, ptrs):
+        arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) if p else None for p in ptrs])
+        return arr
+
+    def bidiagonalize_many_dev(self, a_ptrs, ns, band, d_ptrs, e_ptrs, order=ORDER_PANEL):
+        """Device pointers; stage 2 of matrix i overlaps stage 1 of matrix i+1."""
+        cnt = len(a_ptrs)
+        na = (ctypes.c_size_t * cnt)(*[int(x) for x in ns])
+        self._check(self._fn("bidiagonalize_many_dev")(self.h, Z(cnt), self._ptr_arrays(a_ptrs), na, Z(band), ctypes.c_int(order),
+                                                       self._ptr_arrays(d_ptrs), self._ptr_arrays(e_ptrs)))
+
+    def bidiagonalize_many_inplace(self, a_ptrs, ns, band, d_ptrs, e_ptrs, order=ORDER_PANEL):
+        """Host pointers (raw addresses of caller-owned, ideally pinned, buffers)."""
+        cnt = len(a_ptrs)
+        na = (ctypes.c_size_t * cnt)(*[int(x) for x in ns])
+        self._check(self._fn("bidiagonalize_many")(self.h, Z(cnt), self._ptr_arrays(a_ptrs), na, Z(band), ctypes.c_int(order),
+                                                   self._ptr_arrays(d_ptrs), self._ptr_arrays(e_ptrs)))
+
     def set_profile(self, on):
         self._check(lib().svdb200_set_profile(self.h, ctypes.c_int(1 if on else 0)))
 

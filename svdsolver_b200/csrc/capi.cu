@@ -282,6 +282,155 @@ int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma)
 template int batched_svdvals<float>(Ctx*, float*, size_t, size_t, size_t, float*);
 template int batched_svdvals<double>(Ctx*, double*, size_t, size_t, size_t, double*);
 
+// Pipelined driver for a list of independent matrices (different sizes allowed): stage 2 of matrix i runs on its own
+// stream beside stage 1 of matrix i+1 -- and beside stage 2 of matrix i-1: up to Ctx::kLanes sweep pipelines are in
+// flight.  Both stages are latency-bound at moderate n (a bulge-chasing sweep pipeline uses n/(2b)+2 CTAs, a panel
+// factorisation one cluster), so together they fill a B200 much better than one after the other.
+// Stage 1 is restricted to kernels without cross-cluster / grid-wide waits while a stage-2 kernel may be resident
+// (Ctx::overlap_safe): such kernels need all their CTAs co-resident, which the cooperative stage-2 grids could prevent.
+// The stage-2 grids themselves always fit together (kLanes x (n/(2b)+2) CTAs <= 148 for n <= kOverlapMaxN at band >= 32;
+// for narrower bands the second lane is not used).  Matrices larger than kOverlapMaxN are processed without overlap.
+constexpr size_t kOverlapMaxN = 4096;
+
+static int ensure_s2(Ctx* c) {
+    if (c->s2_stream[0]) return 0;
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        SVDB_CHECK(c, cudaStreamCreateWithFlags(&c->s2_stream[l], cudaStreamNonBlocking));
+        if (l == 0) c->s2_prog[l] = c->prog;
+        else SVDB_CHECK(c, cudaMalloc(&c->s2_prog[l], sizeof(int) * (c->max_n + 8)));
+    }
+    for (auto& e : c->s2ev) SVDB_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+// lanes usable for this matrix: two sweep pipelines must be co-resident beside each other
+static int lanes_for(Ctx* c, size_t n, size_t band) {
+    const size_t ctas = n / band / 2 + 2;
+    return (2 * ctas <= (size_t)c->num_sms - 8) ? Ctx::kLanes : 1;
+}
+
+template <typename T>
+static int run_stage2_on_lane(Ctx* c, int lane, T* a, size_t n, size_t band, T* d, T* e) {
+    cudaStream_t s0 = c->stream;
+    int* p0 = c->prog;
+    c->stream = c->s2_stream[lane];
+    c->prog = c->s2_prog[lane];
+    const int st = stage2_chase<T>(c, a, n, band, d, e);
+    c->stream = s0;
+    c->prog = p0;
+    return st;
+}
+
+template <typename T>
+int bidiagonalize_many_dev(Ctx* c, size_t count, T* const* a, const size_t* n, size_t band, int order, T* const* d, T* const* e) {
+    if (count == 0) return 0;
+    SVDB_TRY(ensure_s2(c));
+    cudaStream_t s0 = c->stream;
+    SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));                  // the lanes see everything enqueued on the caller's stream
+    for (int l = 0; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
+    int st = 0, lane = 0;
+    for (size_t i = 0; i < count && st == 0; ++i) {
+        const bool overlap = order == SVDB200_ORDER_PANEL && n[i] <= kOverlapMaxN && !c->profile;
+        const int nl = overlap ? lanes_for(c, n[i], band) : 1;
+        if (!overlap || nl == 1) {
+            // an unrestricted stage 1 must not meet a stage-2 kernel; a single-lane matrix not a second sweep pipeline
+            for (int l = 0; l < Ctx::kLanes; ++l) {
+                SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
+                if (!overlap) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
+            }
+        }
+        c->overlap_safe = overlap ? 1 : 0;
+        st = order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, a[i], n[i], band) : stage1_tile_order<T>(c, a[i], n[i], band);
+        c->overlap_safe = 0;
+        if (st != 0) break;
+        lane = nl == 1 ? 0 : (lane + 1) % Ctx::kLanes;
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[2], s0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[lane], c->s2ev[2], 0));
+        if (nl == 1)                                                  // wait for the other lanes' sweep pipelines to drain
+            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[0], c->s2ev[4 + l], 0));
+        st = run_stage2_on_lane<T>(c, lane, a[i], n[i], band, d ? d[i] : nullptr, e ? e[i] : nullptr);
+        if (nl == 1) {                                                // and keep them off until this one is done
+            SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->s2_stream[0]));
+            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[1], 0));
+        }
+    }
+    for (int l = 0; l < Ctx::kLanes; ++l) {                          // join
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
+        SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
+    }
+    return st;
+}
+template int bidiagonalize_many_dev<float>(Ctx*, size_t, float* const*, const size_t*, size_t, int, float* const*, float* const*);
+template int bidiagonalize_many_dev<double>(Ctx*, size_t, double* const*, const size_t*, size_t, int, double* const*, double* const*);
+
+// Host-pointer variant: kLanes + 1 staging buffers, so the H2D copy of matrix i+1 and the D2H copies of the matrices still
+// in stage 2 overlap the kernels as well.  a[i] is overwritten by the bidiagonalised matrix, d[i] / e[i] receive the
+// bidiagonal.
+template <typename T>
+int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, size_t band, int order, T* const* d, T* const* e) {
+    if (count == 0) return 0;
+    SVDB_TRY(ensure_s2(c));
+    constexpr int NB = Ctx::kLanes + 1;
+    if (!c->a_dev) SVDB_CHECK(c, cudaMalloc(&c->a_dev, c->esz * c->max_n * c->max_n));
+    c->a_stage[0] = c->a_dev;
+    for (int k = 1; k < NB; ++k)
+        if (!c->a_stage[k]) SVDB_CHECK(c, cudaMalloc(&c->a_stage[k], c->esz * c->max_n * c->max_n));
+    if (!c->de2) SVDB_CHECK(c, cudaMalloc(&c->de2, c->esz * 2 * NB * (c->max_n + 8)));
+    cudaStream_t s0 = c->stream;
+    cudaEvent_t ev_free[NB];                                          // buffer k is free again (its D2H copies have finished)
+    for (auto& ev : ev_free) SVDB_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));
+    for (int l = 0; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
+    int st = 0, lane = 0;
+    for (size_t i = 0; i < count && st == 0; ++i) {
+        const int k = (int)(i % NB);
+        const size_t ni = n[i];
+        T* buf = reinterpret_cast<T*>(c->a_stage[k]);
+        T* dd = reinterpret_cast<T*>(c->de2) + (size_t)2 * k * (c->max_n + 8);
+        T* ee = dd + (c->max_n + 8);
+        const bool overlap = order == SVDB200_ORDER_PANEL && ni <= kOverlapMaxN && !c->profile;
+        const int nl = overlap ? lanes_for(c, ni, band) : 1;
+        if (i >= (size_t)NB) SVDB_CHECK(c, cudaStreamWaitEvent(s0, ev_free[k], 0));
+        SVDB_CHECK(c, cudaMemcpyAsync(buf, a[i], sizeof(T) * ni * ni, cudaMemcpyHostToDevice, s0));
+        if (!overlap || nl == 1) {
+            for (int l = 0; l < Ctx::kLanes; ++l) {
+                SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
+                if (!overlap) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
+            }
+        }
+        c->overlap_safe = overlap ? 1 : 0;
+        st = order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, buf, ni, band) : stage1_tile_order<T>(c, buf, ni, band);
+        c->overlap_safe = 0;
+        if (st != 0) break;
+        lane = nl == 1 ? 0 : (lane + 1) % Ctx::kLanes;
+        cudaStream_t sl = c->s2_stream[lane];
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[2], s0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(sl, c->s2ev[2], 0));
+        if (nl == 1)
+            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[0], c->s2ev[4 + l], 0));
+        st = run_stage2_on_lane<T>(c, lane, buf, ni, band, dd, ee);
+        if (st != 0) break;
+        if (nl == 1) {
+            SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->s2_stream[0]));
+            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[1], 0));
+        }
+        SVDB_CHECK(c, cudaMemcpyAsync(a[i], buf, sizeof(T) * ni * ni, cudaMemcpyDeviceToHost, sl));
+        if (d && d[i]) SVDB_CHECK(c, cudaMemcpyAsync(d[i], dd, sizeof(T) * ni, cudaMemcpyDeviceToHost, sl));
+        if (e && e[i]) SVDB_CHECK(c, cudaMemcpyAsync(e[i], ee, sizeof(T) * (ni - 1), cudaMemcpyDeviceToHost, sl));
+        SVDB_CHECK(c, cudaEventRecord(ev_free[k], sl));
+    }
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
+        SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
+    }
+    cudaError_t es = cudaStreamSynchronize(s0);                       // host buffers are valid on return
+    for (auto& ev : ev_free) cudaEventDestroy(ev);
+    if (st == 0 && es != cudaSuccess) return cuda_status(c, es, "cudaStreamSynchronize");
+    return st;
+}
+template int bidiagonalize_many_host<float>(Ctx*, size_t, float* const*, const size_t*, size_t, int, float* const*, float* const*);
+template int bidiagonalize_many_host<double>(Ctx*, size_t, double* const*, const size_t*, size_t, int, double* const*, double* const*);
+
 }  // namespace svdb200
 
 // ======================================================================================================
@@ -472,11 +621,15 @@ int svdb200_destroy(svdb200_handle h) {
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
-                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws};
+                    c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws, c->de2};
+    for (int k = 1; k <= Ctx::kLanes; ++k) if (c->a_stage[k]) cudaFree(c->a_stage[k]);
+    for (int l = 1; l < Ctx::kLanes; ++l) if (c->s2_prog[l]) cudaFree(c->s2_prog[l]);
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);
     for (auto& e : c->lev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->s2ev) if (e) cudaEventDestroy(e);
+    for (auto& st2 : c->s2_stream) if (st2) cudaStreamDestroy(st2);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -555,6 +708,26 @@ int svdb200_synchronize(svdb200_handle h) {
         SVDB_TRY(check_square(c, m, n, band, dtype_of<T>()));                                                            \
         SVDB_TRY(stage1_dispatch<T>(c, a, n, band, order));                                                              \
         return stage2_chase<T>(c, a, n, band, d, e);                                                                     \
+    }                                                                                                                    \
+    int svdb200_bidiagonalize_many_dev_##S(svdb200_handle h, size_t count, T* const* a, const size_t* n, size_t band,    \
+                                           int order, T* const* d, T* const* e) {                                        \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !n) return SVDB200_E_ARG;                                                                              \
+        for (size_t i = 0; i < count; ++i) {                                                                             \
+            if (!a[i]) return SVDB200_E_ARG;                                                                             \
+            SVDB_TRY(check_square(c, n[i], n[i], band, dtype_of<T>()));                                                  \
+        }                                                                                                                \
+        return bidiagonalize_many_dev<T>(c, count, a, n, band, order, d, e);                                             \
+    }                                                                                                                    \
+    int svdb200_bidiagonalize_many_##S(svdb200_handle h, size_t count, T* const* a, const size_t* n, size_t band,        \
+                                       int order, T* const* d, T* const* e) {                                            \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !n) return SVDB200_E_ARG;                                                                              \
+        for (size_t i = 0; i < count; ++i) {                                                                             \
+            if (!a[i]) return SVDB200_E_ARG;                                                                             \
+            SVDB_TRY(check_square(c, n[i], n[i], band, dtype_of<T>()));                                                  \
+        }                                                                                                                \
+        return bidiagonalize_many_host<T>(c, count, a, n, band, order, d, e);                                            \
     }                                                                                                                    \
     int svdb200_svdvals_##S(svdb200_handle h, T* a, size_t m, size_t n, size_t band, int order, T* sigma) {              \
         SVDB_ENTER(T)                                                                                                    \

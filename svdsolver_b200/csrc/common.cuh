@@ -65,6 +65,14 @@ struct Ctx {
     int use_tc05 = 1;                       // 0 off, 1 when the update is large enough, 2 always (tests)
     long long tc05_min_elems = 8LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
     // singular values of the bidiagonal: 0 auto (zero-shift QR up to qr_auto_limit, bisection above), 1 QR, 2 bisection
+    // pipelined multi-matrix driver (bidiagonalize_many): stage 2 of matrix i on s2_stream beside stage 1 of matrix i+1
+    static constexpr int kLanes = 2;        // stage-2 kernels in flight (n <= 4096: two sweep pipelines fit the 148 SMs)
+    cudaStream_t s2_stream[kLanes] = {};
+    int* s2_prog[kLanes] = {};              // progress counters per lane
+    cudaEvent_t s2ev[4 + kLanes] = {};
+    int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
+    void* a_stage[kLanes + 1] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
+    void* de2 = nullptr;
     int stage2_complete = 0;                // 0: the reference's window schedule (parity), 1: complete chase
     int qr_method = 0;
     size_t qr_auto_limit = 1024;

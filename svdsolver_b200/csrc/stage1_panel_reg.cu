@@ -505,6 +505,9 @@ int launch_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
     constexpr int ROWS = RPT * kWarps;
     const int G = (m + ROWS - 1) / ROWS;
     if (G > c->num_sms || G > kMaxPanelCtas) return 1;
+    // beside a running stage-2 kernel (bidiagonalize_many) only single-cluster launches are allowed: kernels whose
+    // clusters / CTAs wait for each other need all of them co-resident, which a concurrent cooperative kernel can prevent
+    if (c->overlap_safe && (!c->cluster_ok || G > c->cluster_ok)) return 1;
     const size_t smem = reg_smem_bytes(ROWS, b, sizeof(T));
     T* red = reinterpret_cast<T*>(c->red);
     unsigned* bar = c->bar;
@@ -590,7 +593,7 @@ int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaSt
     // rows per CTA = 8 * RPT: the smallest slice that still fits the panel into 128 co-resident CTAs (eight 16-CTA
     // clusters), so that the per-column register pass shrinks with the panel height
     // (double only: in float the column loop is bound by the exchange, and more CTAs only add participants)
-    const int cap = sizeof(T) == 8 ? 128 : 0;
+    const int cap = (sizeof(T) == 8 && !c->overlap_safe) ? 128 : 0;
     if (b <= 32) {
         if (m <= cap * 64) return launch_reg<T, kTrans, 8, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
         if (m <= cap * 128) return launch_reg<T, kTrans, 16, 1>(c, a, lda, m, b, V, V2, stream, cooperative);

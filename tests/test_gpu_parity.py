@@ -417,3 +417,50 @@ def test_svdvals_complete_schedule_matches_lapack(capi, suf, n, b):
     assert np.abs(sig.astype(np.float64) - s0).max() <= tol * s0[0]
     if sigb is not None:
         assert np.abs(sigb[1].astype(np.float64) - s0).max() <= tol * s0[0]
+
+
+# ------------------------------------------------------------------ pipelined multi-matrix driver -------------------------
+@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_bidiagonalize_many_matches_single_calls(capi, oracle, suf, schedule):
+    """svdb200_bidiagonalize_many_*: stage 2 of matrix i beside stage 1 of matrix i+1 (and double-buffered copies in the
+    host variant) -- same results as one call per matrix, for a list of different sizes."""
+    import torch
+    b = 32
+    sizes = [320, 96, 640, 128, 512, 1280, 64]
+    mats = [uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf]) for n in sizes]
+    tdt = torch.float32 if suf == "f32" else torch.float64
+    with handle(capi, max(sizes), b, suf) as h:
+        h.set_stage2_schedule(schedule)
+        singles = [h.bidiagonalize(m.copy(), b) for m in mats]
+        # device variant
+        dev = [torch.from_numpy(m.copy()).cuda() for m in mats]
+        dd = [torch.zeros(n, device="cuda", dtype=tdt) for n in sizes]
+        ee = [torch.zeros(n, device="cuda", dtype=tdt) for n in sizes]
+        torch.cuda.synchronize()
+        h.bidiagonalize_many_dev([x.data_ptr() for x in dev], sizes, b, [x.data_ptr() for x in dd], [x.data_ptr() for x in ee])
+        h.synchronize()
+        # host variant (pinned buffers)
+        host = [torch.from_numpy(m.copy()).pin_memory() for m in mats]
+        hd = [torch.zeros(n, dtype=tdt).pin_memory() for n in sizes]
+        he = [torch.zeros(n, dtype=tdt).pin_memory() for n in sizes]
+        h.bidiagonalize_many_inplace([x.data_ptr() for x in host], sizes, b, [x.data_ptr() for x in hd], [x.data_ptr() for x in he])
+    for i, n in enumerate(sizes):
+        _, d1, e1 = singles[i]
+        scale = float(np.abs(d1).max())
+        # Stage 1 rounds differently beside a stage-2 kernel (fixed slices in double).  The reference's stage-2 schedule
+        # (0) amplifies that without bound towards the end of the bidiagonal (SURVEY 0.7: 1.5e-4 at n = 1280), so beyond
+        # n = 512 only the complete schedule (1), which is stable, is compared element by element.
+        if schedule == 0 and n > 512:
+            continue
+        tol = (TOL[suf] if schedule == 0 else (1e-3 if suf == "f32" else 1e-9)) * scale
+        for dgot, egot in ((dd[i].cpu().numpy(), ee[i].cpu().numpy()), (hd[i].numpy(), he[i].numpy())):
+            assert np.abs(dgot - d1).max() <= tol
+            assert np.abs(egot[:n - 1] - e1).max() <= tol
+        assert np.abs(np.diagonal(host[i].numpy()) - hd[i].numpy()).max() == 0          # matrix copied back
+    # and against the oracle chain for one of them (double)
+    if suf == "f64" and schedule == 0:
+        i = sizes.index(320)
+        band = oracle.brd_p1_panel(mats[i], b)
+        _, dr, er = oracle.brd_p2(band, b)
+        assert np.abs(dd[i].cpu().numpy() - dr).max() <= 1e-10 * np.abs(dr).max()
