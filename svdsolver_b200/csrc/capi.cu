@@ -298,27 +298,85 @@ static int ensure_s2(Ctx* c) {
         SVDB_CHECK(c, cudaStreamCreateWithFlags(&c->s2_stream[l], cudaStreamNonBlocking));
         if (l == 0) c->s2_prog[l] = c->prog;
         else SVDB_CHECK(c, cudaMalloc(&c->s2_prog[l], sizeof(int) * (c->max_n + 8)));
+        svdb200_handle h = nullptr;                                   // stage-1 sub-handle: own reflector / W workspace and streams
+        int st = svdb200_create(&h, c->device, c->max_n, c->band, c->dtype);
+        if (st != 0) return st;
+        c->s1ctx[l] = reinterpret_cast<Ctx*>(h);
     }
     for (auto& e : c->s2ev) SVDB_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
 }
 
-// lanes usable for this matrix: two sweep pipelines must be co-resident beside each other
+// chains usable for this matrix: their sweep pipelines must be co-resident beside each other
 static int lanes_for(Ctx* c, size_t n, size_t band) {
-    const size_t ctas = n / band / 2 + 2;
-    return (2 * ctas <= (size_t)c->num_sms - 8) ? Ctx::kLanes : 1;
+    const size_t ctas = n / band / 2 + 2;                             // CTAs of one sweep pipeline, all of which must be resident
+    const size_t budget = (size_t)c->num_sms * 5 / 2;                 // 3 light stage-2 CTAs fit an SM; leave room for stage 1
+    const size_t cap = c->pipe_light ? budget : (size_t)c->num_sms - 8;        // the 153-register variant: one CTA per SM
+    return ((size_t)c->lanes * ctas <= cap) ? c->lanes : 1;
 }
 
 template <typename T>
 static int run_stage2_on_lane(Ctx* c, int lane, T* a, size_t n, size_t band, T* d, T* e) {
     cudaStream_t s0 = c->stream;
     int* p0 = c->prog;
+    const int light0 = c->stage2_light;
     c->stream = c->s2_stream[lane];
     c->prog = c->s2_prog[lane];
+    c->stage2_light = c->pipe_light ? 1 : light0;
     const int st = stage2_chase<T>(c, a, n, band, d, e);
     c->stream = s0;
     c->prog = p0;
+    c->stage2_light = light0;
     return st;
+}
+
+// every stream of the pipeline has finished what was enqueued so far, as seen from `into`
+static int drain_into(Ctx* c, cudaStream_t into) {
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
+        SVDB_CHECK(c, cudaStreamWaitEvent(into, c->s2ev[4 + l], 0));
+        SVDB_CHECK(c, cudaEventRecord(c->s1ctx[l]->lev[0], c->s1ctx[l]->stream));
+        SVDB_CHECK(c, cudaStreamWaitEvent(into, c->s1ctx[l]->lev[0], 0));
+    }
+    return 0;
+}
+
+// One matrix through the pipeline.  Chain k = i % lanes: stage 1 on sub-handle k's streams, stage 2 on lane k -- so `lanes`
+// stage-1 factorizations and `lanes` sweep pipelines are in flight (default 2; 4 measured slower: contention); within a chain stage 1 of the next matrix starts as soon
+// as the previous stage 1 is done, beside that matrix's stage 2.  `h2d` (host variant): copy issued on the chain's stream.
+template <typename T>
+static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, size_t band, int order, T* d, T* e, cudaStream_t* lane_out) {
+    const bool overlap = order == SVDB200_ORDER_PANEL && n <= kOverlapMaxN && !c->profile;
+    const int nl = overlap ? lanes_for(c, n, band) : 1;
+    if (!overlap || nl == 1) {
+        // no overlap: wait for everything, run on the parent handle, and hold the pipeline back until it is done
+        SVDB_TRY(drain_into(c, c->stream));
+        if (a_host) SVDB_CHECK(c, cudaMemcpyAsync(a_dev, a_host, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream));
+        SVDB_TRY(order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, a_dev, n, band) : stage1_tile_order<T>(c, a_dev, n, band));
+        SVDB_TRY(stage2_chase<T>(c, a_dev, n, band, d, e));
+        SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->stream));
+        for (int l = 0; l < Ctx::kLanes; ++l) {
+            SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[1], 0));
+            SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[1], 0));
+        }
+        *lane_out = c->stream;
+        return 0;
+    }
+    const int k = (int)(i % (size_t)c->lanes);
+    Ctx* s = c->s1ctx[k];
+    s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems; s->lookahead = c->lookahead;
+    s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
+    if (a_host) SVDB_CHECK(c, cudaMemcpyAsync(a_dev, a_host, sizeof(T) * n * n, cudaMemcpyHostToDevice, s->stream));
+    s->overlap_safe = 1;
+    int st = stage1_panel_order<T>(s, a_dev, n, band);
+    s->overlap_safe = 0;
+    c->launches += s->launches; s->launches = 0;
+    if (st != 0) { c->last_error = s->last_error; return st; }
+    SVDB_CHECK(c, cudaEventRecord(s->lev[0], s->stream));
+    SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[k], s->lev[0], 0));
+    SVDB_TRY(run_stage2_on_lane<T>(c, k, a_dev, n, band, d, e));
+    *lane_out = c->s2_stream[k];
+    return 0;
 }
 
 template <typename T>
@@ -326,105 +384,65 @@ int bidiagonalize_many_dev(Ctx* c, size_t count, T* const* a, const size_t* n, s
     if (count == 0) return 0;
     SVDB_TRY(ensure_s2(c));
     cudaStream_t s0 = c->stream;
-    SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));                  // the lanes see everything enqueued on the caller's stream
-    for (int l = 0; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
-    int st = 0, lane = 0;
-    for (size_t i = 0; i < count && st == 0; ++i) {
-        const bool overlap = order == SVDB200_ORDER_PANEL && n[i] <= kOverlapMaxN && !c->profile;
-        const int nl = overlap ? lanes_for(c, n[i], band) : 1;
-        if (!overlap || nl == 1) {
-            // an unrestricted stage 1 must not meet a stage-2 kernel; a single-lane matrix not a second sweep pipeline
-            for (int l = 0; l < Ctx::kLanes; ++l) {
-                SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
-                if (!overlap) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
-            }
-        }
-        c->overlap_safe = overlap ? 1 : 0;
-        st = order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, a[i], n[i], band) : stage1_tile_order<T>(c, a[i], n[i], band);
-        c->overlap_safe = 0;
-        if (st != 0) break;
-        lane = nl == 1 ? 0 : (lane + 1) % Ctx::kLanes;
-        SVDB_CHECK(c, cudaEventRecord(c->s2ev[2], s0));
-        SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[lane], c->s2ev[2], 0));
-        if (nl == 1)                                                  // wait for the other lanes' sweep pipelines to drain
-            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[0], c->s2ev[4 + l], 0));
-        st = run_stage2_on_lane<T>(c, lane, a[i], n[i], band, d ? d[i] : nullptr, e ? e[i] : nullptr);
-        if (nl == 1) {                                                // and keep them off until this one is done
-            SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->s2_stream[0]));
-            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[1], 0));
-        }
+    SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));                  // the pipeline sees everything enqueued on the caller's stream
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[0], 0));
     }
-    for (int l = 0; l < Ctx::kLanes; ++l) {                          // join
-        SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
-        SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
+    for (size_t i = 0; i < count; ++i) {
+        cudaStream_t lane;
+        SVDB_TRY(pipeline_one<T>(c, i, a[i], (const T*)nullptr, n[i], band, order, d ? d[i] : nullptr, e ? e[i] : nullptr, &lane));
     }
-    return st;
+    return drain_into(c, s0);                                         // join
 }
 template int bidiagonalize_many_dev<float>(Ctx*, size_t, float* const*, const size_t*, size_t, int, float* const*, float* const*);
 template int bidiagonalize_many_dev<double>(Ctx*, size_t, double* const*, const size_t*, size_t, int, double* const*, double* const*);
 
-// Host-pointer variant: kLanes + 1 staging buffers, so the H2D copy of matrix i+1 and the D2H copies of the matrices still
-// in stage 2 overlap the kernels as well.  a[i] is overwritten by the bidiagonalised matrix, d[i] / e[i] receive the
-// bidiagonal.
+// Host-pointer variant: 2 * kLanes staging buffers (two per chain), so the H2D copy of a chain's next matrix and the D2H
+// copy of its previous one overlap the kernels as well.  a[i] is overwritten by the bidiagonalised matrix, d[i] / e[i]
+// receive the bidiagonal.
 template <typename T>
 int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, size_t band, int order, T* const* d, T* const* e) {
     if (count == 0) return 0;
     SVDB_TRY(ensure_s2(c));
-    constexpr int NB = Ctx::kLanes + 1;
+    constexpr int NBmax = 2 * Ctx::kLanes;
+    const int NB = 2 * c->lanes;
     if (!c->a_dev) SVDB_CHECK(c, cudaMalloc(&c->a_dev, c->esz * c->max_n * c->max_n));
     c->a_stage[0] = c->a_dev;
     for (int k = 1; k < NB; ++k)
         if (!c->a_stage[k]) SVDB_CHECK(c, cudaMalloc(&c->a_stage[k], c->esz * c->max_n * c->max_n));
-    if (!c->de2) SVDB_CHECK(c, cudaMalloc(&c->de2, c->esz * 2 * NB * (c->max_n + 8)));
+    if (!c->de2) SVDB_CHECK(c, cudaMalloc(&c->de2, c->esz * 2 * NBmax * (c->max_n + 8)));
     cudaStream_t s0 = c->stream;
-    cudaEvent_t ev_free[NB];                                          // buffer k is free again (its D2H copies have finished)
+    cudaEvent_t ev_free[NBmax];                                          // buffer k is free again (its D2H copies have finished)
     for (auto& ev : ev_free) SVDB_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));
-    for (int l = 0; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
-    int st = 0, lane = 0;
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
+        SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[0], 0));
+    }
+    int st = 0;
     for (size_t i = 0; i < count && st == 0; ++i) {
-        const int k = (int)(i % NB);
+        const int k = (int)(i % NB);                                  // chain i % kLanes alternates between its two buffers
         const size_t ni = n[i];
         T* buf = reinterpret_cast<T*>(c->a_stage[k]);
         T* dd = reinterpret_cast<T*>(c->de2) + (size_t)2 * k * (c->max_n + 8);
         T* ee = dd + (c->max_n + 8);
-        const bool overlap = order == SVDB200_ORDER_PANEL && ni <= kOverlapMaxN && !c->profile;
-        const int nl = overlap ? lanes_for(c, ni, band) : 1;
-        if (i >= (size_t)NB) SVDB_CHECK(c, cudaStreamWaitEvent(s0, ev_free[k], 0));
-        SVDB_CHECK(c, cudaMemcpyAsync(buf, a[i], sizeof(T) * ni * ni, cudaMemcpyHostToDevice, s0));
-        if (!overlap || nl == 1) {
-            for (int l = 0; l < Ctx::kLanes; ++l) {
-                SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
-                if (!overlap) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
-            }
+        if (i >= (size_t)NB) {                                        // the copy into the buffer is issued on the chain's stage-1 stream
+            SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[i % (size_t)c->lanes]->stream, ev_free[k], 0));
+            SVDB_CHECK(c, cudaStreamWaitEvent(s0, ev_free[k], 0));
         }
-        c->overlap_safe = overlap ? 1 : 0;
-        st = order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, buf, ni, band) : stage1_tile_order<T>(c, buf, ni, band);
-        c->overlap_safe = 0;
+        cudaStream_t lane = s0;
+        st = pipeline_one<T>(c, i, buf, a[i], ni, band, order, dd, ee, &lane);
         if (st != 0) break;
-        lane = nl == 1 ? 0 : (lane + 1) % Ctx::kLanes;
-        cudaStream_t sl = c->s2_stream[lane];
-        SVDB_CHECK(c, cudaEventRecord(c->s2ev[2], s0));
-        SVDB_CHECK(c, cudaStreamWaitEvent(sl, c->s2ev[2], 0));
-        if (nl == 1)
-            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[0], c->s2ev[4 + l], 0));
-        st = run_stage2_on_lane<T>(c, lane, buf, ni, band, dd, ee);
-        if (st != 0) break;
-        if (nl == 1) {
-            SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->s2_stream[0]));
-            for (int l = 1; l < Ctx::kLanes; ++l) SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[1], 0));
-        }
-        SVDB_CHECK(c, cudaMemcpyAsync(a[i], buf, sizeof(T) * ni * ni, cudaMemcpyDeviceToHost, sl));
-        if (d && d[i]) SVDB_CHECK(c, cudaMemcpyAsync(d[i], dd, sizeof(T) * ni, cudaMemcpyDeviceToHost, sl));
-        if (e && e[i]) SVDB_CHECK(c, cudaMemcpyAsync(e[i], ee, sizeof(T) * (ni - 1), cudaMemcpyDeviceToHost, sl));
-        SVDB_CHECK(c, cudaEventRecord(ev_free[k], sl));
+        SVDB_CHECK(c, cudaMemcpyAsync(a[i], buf, sizeof(T) * ni * ni, cudaMemcpyDeviceToHost, lane));
+        if (d && d[i]) SVDB_CHECK(c, cudaMemcpyAsync(d[i], dd, sizeof(T) * ni, cudaMemcpyDeviceToHost, lane));
+        if (e && e[i]) SVDB_CHECK(c, cudaMemcpyAsync(e[i], ee, sizeof(T) * (ni - 1), cudaMemcpyDeviceToHost, lane));
+        SVDB_CHECK(c, cudaEventRecord(ev_free[k], lane));
     }
-    for (int l = 0; l < Ctx::kLanes; ++l) {
-        SVDB_CHECK(c, cudaEventRecord(c->s2ev[4 + l], c->s2_stream[l]));
-        SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->s2ev[4 + l], 0));
-    }
+    int sj = drain_into(c, s0);
     cudaError_t es = cudaStreamSynchronize(s0);                       // host buffers are valid on return
     for (auto& ev : ev_free) cudaEventDestroy(ev);
+    if (st == 0 && sj != 0) return sj;
     if (st == 0 && es != cudaSuccess) return cuda_status(c, es, "cudaStreamSynchronize");
     return st;
 }
@@ -587,6 +605,12 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (la && la[0] == '0') c->lookahead = 0;
         const char* pr = getenv("SVDB200_PANEL_REG");
         if (pr && pr[0] == '0') c->panel_reg = 0;
+        const char* ln = getenv("SVDB200_LANES");
+        if (ln && ln[0] >= '1' && ln[0] <= '4') c->lanes = ln[0] - '0';
+        const char* pl = getenv("SVDB200_PIPE_LIGHT");
+        if (pl && pl[0] == '1') c->pipe_light = 1;
+        const char* s2l = getenv("SVDB200_S2_LIGHT");
+        if (s2l && s2l[0] == '1') c->stage2_light = 1;
         const char* prm = getenv("SVDB200_PANEL_REG_MIN");
         if (prm && prm[0]) c->panel_reg_min = atoi(prm);
     }
@@ -622,7 +646,8 @@ int svdb200_destroy(svdb200_handle h) {
     c->pool.clear();
     void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws, c->de2};
-    for (int k = 1; k <= Ctx::kLanes; ++k) if (c->a_stage[k]) cudaFree(c->a_stage[k]);
+    for (int k = 1; k < 2 * Ctx::kLanes; ++k) if (c->a_stage[k]) cudaFree(c->a_stage[k]);
+    for (int l = 0; l < Ctx::kLanes; ++l) if (c->s1ctx[l]) svdb200_destroy(reinterpret_cast<svdb200_handle>(c->s1ctx[l]));
     for (int l = 1; l < Ctx::kLanes; ++l) if (c->s2_prog[l]) cudaFree(c->s2_prog[l]);
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);

@@ -66,13 +66,18 @@ struct Ctx {
     long long tc05_min_elems = 8LL << 20;   // smallest M*N the tcgen05 kernels are used for in mode 1
     // singular values of the bidiagonal: 0 auto (zero-shift QR up to qr_auto_limit, bisection above), 1 QR, 2 bisection
     // pipelined multi-matrix driver (bidiagonalize_many): stage 2 of matrix i on s2_stream beside stage 1 of matrix i+1
-    static constexpr int kLanes = 2;        // stage-2 kernels in flight (n <= 4096: two sweep pipelines fit the 148 SMs)
+    int lanes = 2;                          // chains actually used (<= kLanes; SVDB200_LANES)
+    int pipe_light = 0;                     // pipelined driver: light stage-2 variant (SVDB200_PIPE_LIGHT)
+    static constexpr int kLanes = 4;        // chains in flight: each = one stage 1 (own sub-handle) and one stage-2 kernel (85-register
+                                            // variant, 3 CTAs per SM: four sweep pipelines of n <= 4096 fit the GPU beside the stage-1 kernels)
     cudaStream_t s2_stream[kLanes] = {};
     int* s2_prog[kLanes] = {};              // progress counters per lane
     cudaEvent_t s2ev[4 + kLanes] = {};
     int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
-    void* a_stage[kLanes + 1] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
+    Ctx* s1ctx[kLanes] = {};                // sub-handles (own workspace + streams): stage 1 of two matrices at a time
+    void* a_stage[2 * kLanes] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
     void* de2 = nullptr;
+    int stage2_light = 0;                   // single matrix: use the 85-register stage-2 variant (3 CTAs per SM) -- pipelined driver
     int stage2_complete = 0;                // 0: the reference's window schedule (parity), 1: complete chase
     int qr_method = 0;
     size_t qr_auto_limit = 1024;

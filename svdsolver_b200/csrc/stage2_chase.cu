@@ -321,7 +321,7 @@ int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int co
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
     // small bands run with <= 256 threads: instantiate that case without the 64-register cap; a batch wants
     // several CTAs per SM instead (the window product is FP64-issue bound for ~40 % of an op, the rest is latency)
-    auto kern = nt <= 256 ? (count > 1 ? stage2_chase_kernel<T, 256, 3> : stage2_chase_kernel<T, 256, 1>)
+    auto kern = nt <= 256 ? ((count > 1 || c->stage2_light) ? stage2_chase_kernel<T, 256, 3> : stage2_chase_kernel<T, 256, 1>)
                           : stage2_chase_kernel<T, 1024, 1>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
