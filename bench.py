@@ -204,9 +204,16 @@ def north_star_shape(capi, torch, stream, dev, local_rank, dt, peaks, hbm_peak, 
             if pk:
                 out["trailing_update_frac_of_3xtf32_tcgen05_peak"] = round(tf / (pk / 3.0), 4)
             out["tensor_path"] = "tcgen05.mma kind::tf32 x3 (hi/lo split), accumulator in TMEM, operands by TMA"
-        out["classes"] = {k: {"ms": round(x["ms"], 2), "launches": x["launches"],
-                              "tflops": round(x["work"] / (x["ms"] * 1e-3) * 1e-12, 2) if x["ms"] > 0 else None}
-                          for k, x in pb.items() if x["launches"]}
+        def _cls(k, x):
+            o = {"ms": round(x["ms"], 2), "launches": x["launches"],
+                 "tflops": round(x["work"] / (x["ms"] * 1e-3) * 1e-12, 2) if x["ms"] > 0 else None}
+            if k in ("gemm_tn", "gemm_nn", "rank_update") and x["ms"] > 0:
+                # algorithmic HBM bytes: C read once (GEMMs) / read + written once (rank-b update)
+                byts = x["work"] / (2.0 * bb) * esz * (2 if k == "rank_update" else 1)
+                o["hbm_gbs"] = round(byts / (x["ms"] * 1e-3) * 1e-9, 1)
+                o["frac_of_hbm_peak"] = round(o["hbm_gbs"] / hbm_peak, 4)
+            return o
+        out["classes"] = {k: _cls(k, x) for k, x in pb.items() if x["launches"]}
         hb.close()
         del ab
         torch.cuda.empty_cache()
