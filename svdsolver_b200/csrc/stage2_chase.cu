@@ -58,7 +58,17 @@ __host__ __device__ inline int stage2_threads(int c) {
 __device__ __forceinline__ int wait_progress(const int* p, int need, int seen) {
     if (seen >= need) return seen;
     int v;
-    while ((v = ld_acquire(p)) < need) __nanosleep(20);
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    while ((v = ld_acquire(p)) < need) {
+        __nanosleep(20);
+        if ((++polls & 0xfffu) == 0u) {               // a predecessor that never advances must not hang the GPU: trap after 30 s
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 30000000000ull) __trap();
+        }
+    }
     return v;
 }
 
