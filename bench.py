@@ -418,7 +418,7 @@ def main():
                            "stage1_gflops": round(flops(n) / (t1 * 1e-3) * 1e-9, 1)})
 
     # ---- roofline of the dominant kernel: profiled pass, CUDA events per launch ------------------
-    roofline, prof_out, peaks, big, big32, other = None, None, {}, None, None, None
+    roofline, prof_out, peaks, big, big32, other, roofline_ns = None, None, {}, None, None, None, None
     if rank == 0:
         h = handles["f64"]
         peaks = {"dfma_tflops": h.probe_peak(0), "dmma_f64_tflops": h.probe_peak(1), "ffma_tflops": h.probe_peak(2),
@@ -475,6 +475,16 @@ def main():
             big = north_star_shape(capi, torch, stream, dev, local_rank, np.float64, peaks, hbm_peak or 6650.0)
             big32 = north_star_shape(capi, torch, stream, dev, local_rank, np.float32, peaks, hbm_peak or 6650.0)
             other = full_configs(capi, torch, stream, dev, local_rank) if world == 1 else None
+            # second roofline object: the dominant kernel of stage 1 at the north-star shape in float, the tcgen05 rank-b update
+            try:
+                ru = big32["classes"]["rank_update"]
+                roofline_ns = {"bound": "hbm", "kernel": "rank_update_tc05_kernel<64> (C += V2*W on tcgen05/TMEM, C through TMA; n=16384, band 64, float)",
+                               "achieved": ru["hbm_gbs"], "peak": hbm_peak or 6650.0, "unit": "GB/s", "frac": ru["frac_of_hbm_peak"],
+                               "traffic": 2194703000, "traffic_note": "dram read+write of the first (full-size) launch, ncu --set full (profiles/r01_ncu_metrics.csv); algorithmic 2.147e9",
+                               "algorithmic_bytes": "8 bytes per element of the updated block per launch (read once + written once)",
+                               "launches_timed": ru["launches"], "avg_launch_us": round(ru["ms"] / max(ru["launches"], 1) * 1e3, 1)}
+            except Exception:
+                roofline_ns = None
     # ---- e2e: host-pointer C-ABI call with pinned host buffers --------------------------------------
     from svdsolver_b200.synth import uniform_matrix
     e2e = None
@@ -562,7 +572,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_north_star_f32": roofline_ns, "cpu_baseline": cpu,
             "kernel_classes_f64": prof_out, "north_star_shape": big, "north_star_shape_f32": big32, "other_configs": other, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
         }
         print(json.dumps(line), flush=True)
