@@ -319,7 +319,7 @@ rank_update_tc05_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
         Cur pc; pc.item = blockIdx.x; cur_set(pc);
         Cur lc = pc;
         if (leader) {
-            for (int k = 0; k < R - 2 && lc.item < nitems; ++k) {
+            for (int k = 0; k < R - 1 && lc.item < nitems; ++k) {
                 mbar_expect_tx(bCFull + 8 * k, Cfg::kStage);
                 tma_load_2d(sC + k * Cfg::kStage, &tmC, bCFull + 8 * k, lc.t * 128 + lc.j * 32, lc.rb * 128);
                 cur_next(lc);
@@ -357,9 +357,9 @@ rank_update_tc05_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
             if (leader) {
                 tma_store_2d(&tmC, sC + st * Cfg::kStage, pc.t * 128 + pc.j * 32, pc.rb * 128);
                 bulk_commit();
-                bulk_wait_read<2>();               // the store issued two sub-tiles ago has released its stage
+                bulk_wait_read<1>();               // the store issued one sub-tile ago has released its stage
                 if (lc.item < nitems) {
-                    const int ls = (s + R - 2) % R;
+                    const int ls = (s + R - 1) % R;
                     mbar_expect_tx(bCFull + 8 * ls, Cfg::kStage);
                     tma_load_2d(sC + ls * Cfg::kStage, &tmC, bCFull + 8 * ls, lc.t * 128 + lc.j * 32, lc.rb * 128);
                     cur_next(lc);
