@@ -115,7 +115,7 @@ __host__ __device__ inline size_t stage_elems(int rows, int b, int max_cs) {
 }
 
 template <typename T, bool kTrans, bool kCluster, int RPT, int CPL>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 && RPT * CPL <= 32) ? 2 : 1)
 panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, T* __restrict__ red,
                  unsigned* __restrict__ bar, int NC, unsigned epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -380,7 +380,7 @@ panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         // per scheduler a row-by-row order leaves the pass waiting on it (short-scoreboard stalls, prof_r1_panel4).
         // (double: chunks of 8 rows; it runs one CTA per SM with the full register file)
         if constexpr (true) {
-        constexpr int CH = sizeof(T) == 8 ? (RPT < 8 ? RPT : 8) : RPT;
+        constexpr int CH = sizeof(T) == 8 ? (RPT < 8 ? RPT : 8) : (RPT < 32 ? RPT : 32);
         T bc[CH];
 #pragma unroll
         for (int i0 = 0; i0 < RPT; i0 += CH) {
@@ -597,12 +597,17 @@ int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaSt
     if (b <= 32) {
         if (m <= cap * 64) return launch_reg<T, kTrans, 8, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
         if (m <= cap * 128) return launch_reg<T, kTrans, 16, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
-        return launch_reg<T, kTrans, 32, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (sizeof(T) == 8 || m <= 128 * 256) return launch_reg<T, kTrans, 32, 1>(c, a, lda, m, b, V, V2, stream, cooperative);
+        // very tall float panels (multi-GPU stage 1, n = 65536): 512 / 1024 rows per CTA keep the launch within 128 CTAs
+        if (m <= 128 * 512) return launch_reg<float, kTrans, 64, 1>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream, cooperative);
+        return launch_reg<float, kTrans, 128, 1>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream, cooperative);
     }
     if (b <= 64) {
         if (m <= cap * 32) return launch_reg<T, kTrans, 4, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
         if (m <= cap * 64) return launch_reg<T, kTrans, 8, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
-        return launch_reg<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (sizeof(T) == 8 || m <= 128 * 128) return launch_reg<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream, cooperative);
+        if (m <= 128 * 256) return launch_reg<float, kTrans, 32, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream, cooperative);
+        return launch_reg<float, kTrans, 64, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream, cooperative);
     }
     return 1;
 }
