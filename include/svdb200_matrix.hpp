@@ -307,6 +307,9 @@ template <> inline int dense_to_band<double>(svdb200_handle h, double* a, size_t
 template <typename T> int band_to_bidiag(svdb200_handle h, T* a, size_t m, size_t n, size_t b, T* d, T* e);
 template <> inline int band_to_bidiag<float>(svdb200_handle h, float* a, size_t m, size_t n, size_t b, float* d, float* e) { return svdb200_band_to_bidiag_f32(h, a, m, n, b, d, e); }
 template <> inline int band_to_bidiag<double>(svdb200_handle h, double* a, size_t m, size_t n, size_t b, double* d, double* e) { return svdb200_band_to_bidiag_f64(h, a, m, n, b, d, e); }
+template <typename T> int bidiagonalize_many(svdb200_handle h, size_t count, T* const* a, const size_t* n, size_t b, int order, T* const* d, T* const* e);
+template <> inline int bidiagonalize_many<float>(svdb200_handle h, size_t c, float* const* a, const size_t* n, size_t b, int o, float* const* d, float* const* e) { return svdb200_bidiagonalize_many_f32(h, c, a, n, b, o, d, e); }
+template <> inline int bidiagonalize_many<double>(svdb200_handle h, size_t c, double* const* a, const size_t* n, size_t b, int o, double* const* d, double* const* e) { return svdb200_bidiagonalize_many_f64(h, c, a, n, b, o, d, e); }
 template <typename T> int bidiag_qr(svdb200_handle h, const T* d, const T* e, size_t n, T* s, long long* sw);
 template <> inline int bidiag_qr<float>(svdb200_handle h, const float* d, const float* e, size_t n, float* s, long long* sw) { return svdb200_bidiag_qr_f32(h, d, e, n, s, sw); }
 template <> inline int bidiag_qr<double>(svdb200_handle h, const double* d, const double* e, size_t n, double* s, long long* sw) { return svdb200_bidiag_qr_f64(h, d, e, n, s, sw); }
@@ -330,6 +333,29 @@ Matrix<T> brd_p2(Matrix<T>& A, size_t const w) {
     auto h = b200::session<T>().get(A.nrows, w - 1, b200::dtype_code<T>());
     b200::check(b200::band_to_bidiag<T>(h, A.data(), A.nrows, A.ncols, w - 1, nullptr, nullptr), "gpu::brd_p2");
     return A;
+}
+// A list of independent instances, dense -> band -> bidiagonal, handed over together: what the reference's benchmark
+// loop over test instances (timing.h:55-91, svd_cuda_2.cu:1370-1384) becomes when the device may overlap stage 2 of
+// one instance with stage 1 of the next.  Every matrix is overwritten like cuda_brd_p1 + brd_p2 would; the
+// results equal one call per instance.
+template <typename T>
+std::vector<serial::Bidiagonal<T>> cuda_bidiagonalize_many(std::vector<Matrix<T>>& As, size_t const b_size) {
+    std::vector<serial::Bidiagonal<T>> out(As.size());
+    if (As.empty()) return out;
+    std::vector<T*> a(As.size()), d(As.size()), e(As.size());
+    std::vector<size_t> n(As.size());
+    size_t max_n = 0;
+    for (size_t i = 0; i < As.size(); ++i) {
+        assert(As[i].nrows == As[i].ncols && b_size > 0 && As[i].nrows % b_size == 0 && "square matrices with band | n expected");
+        n[i] = As[i].nrows;
+        max_n = std::max(max_n, n[i]);
+        out[i].d.resize(n[i]);
+        out[i].e.resize(n[i] > 0 ? n[i] - 1 : 0);
+        a[i] = As[i].data(); d[i] = out[i].d.data(); e[i] = out[i].e.data();
+    }
+    auto h = b200::session<T>().get(max_n, b_size, b200::dtype_code<T>());
+    b200::check(b200::bidiagonalize_many<T>(h, As.size(), a.data(), n.data(), b_size, SVDB200_ORDER_PANEL, d.data(), e.data()), "cuda_bidiagonalize_many");
+    return out;
 }
 }  // namespace gpu
 
@@ -386,6 +412,16 @@ duration benchmark(Callable f, Container test_instances, size_t const b_size) {
         elapsed += t1 - t0;
     }
     return std::chrono::duration_cast<std::chrono::microseconds>(elapsed).count() / static_cast<duration>(test_instances.size());
+}
+// the same mean for a callable that takes the whole list of instances at once (gpu::cuda_bidiagonalize_many)
+template <typename Callable, typename Container>
+duration benchmark_many(Callable f, Container test_instances, size_t const b_size) {
+    auto x = test_instances;
+    auto const t0 = std::chrono::steady_clock::now();
+    auto out = f(x, b_size);
+    auto const t1 = std::chrono::steady_clock::now();
+    (void)out;
+    return std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() / static_cast<duration>(test_instances.size());
 }
 }  // namespace benchmark
 

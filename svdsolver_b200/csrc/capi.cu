@@ -400,7 +400,17 @@ template int bidiagonalize_many_dev<double>(Ctx*, size_t, double* const*, const 
 
 // Host-pointer variant: 2 * kLanes staging buffers (two per chain), so the H2D copy of a chain's next matrix and the D2H
 // copy of its previous one overlap the kernels as well.  a[i] is overwritten by the bidiagonalised matrix, d[i] / e[i]
-// receive the bidiagonal.
+// receive the bidiagonal.  Pinned (or registered) host buffers get fully asynchronous copies.  A copy INTO pageable memory
+// blocks the calling thread until the stream reaches it, which would serialise the pipeline if it were issued right behind
+// the matrix's stage 2 -- for pageable destinations the copies are therefore issued only when the staging buffer is needed
+// again (NB matrices later) or at the end, while the matrices in between keep the device busy.
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 template <typename T>
 int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, size_t band, int order, T* const* d, T* const* e) {
     if (count == 0) return 0;
@@ -420,6 +430,20 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[0], 0));
     }
+    struct Result { T *a, *d, *e; size_t n; cudaStream_t lane; bool live; } res[NBmax] = {};
+    auto copy_back = [&](int k) -> int {                              // results of the matrix in staging buffer k -> host
+        Result& r = res[k];
+        if (!r.live) return 0;
+        r.live = false;
+        T* buf = reinterpret_cast<T*>(c->a_stage[k]);
+        T* dd = reinterpret_cast<T*>(c->de2) + (size_t)2 * k * (c->max_n + 8);
+        T* ee = dd + (c->max_n + 8);
+        SVDB_CHECK(c, cudaMemcpyAsync(r.a, buf, sizeof(T) * r.n * r.n, cudaMemcpyDeviceToHost, r.lane));
+        if (r.d) SVDB_CHECK(c, cudaMemcpyAsync(r.d, dd, sizeof(T) * r.n, cudaMemcpyDeviceToHost, r.lane));
+        if (r.e) SVDB_CHECK(c, cudaMemcpyAsync(r.e, ee, sizeof(T) * (r.n - 1), cudaMemcpyDeviceToHost, r.lane));
+        SVDB_CHECK(c, cudaEventRecord(ev_free[k], r.lane));
+        return 0;
+    };
     int st = 0;
     for (size_t i = 0; i < count && st == 0; ++i) {
         const int k = (int)(i % NB);                                  // chain i % kLanes alternates between its two buffers
@@ -427,6 +451,7 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         T* buf = reinterpret_cast<T*>(c->a_stage[k]);
         T* dd = reinterpret_cast<T*>(c->de2) + (size_t)2 * k * (c->max_n + 8);
         T* ee = dd + (c->max_n + 8);
+        if ((st = copy_back(k)) != 0) break;                          // a deferred (pageable) result still sitting in this buffer
         if (i >= (size_t)NB) {                                        // the copy into the buffer is issued on the chain's stage-1 stream
             SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[i % (size_t)c->lanes]->stream, ev_free[k], 0));
             SVDB_CHECK(c, cudaStreamWaitEvent(s0, ev_free[k], 0));
@@ -434,11 +459,11 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         cudaStream_t lane = s0;
         st = pipeline_one<T>(c, i, buf, a[i], ni, band, order, dd, ee, &lane);
         if (st != 0) break;
-        SVDB_CHECK(c, cudaMemcpyAsync(a[i], buf, sizeof(T) * ni * ni, cudaMemcpyDeviceToHost, lane));
-        if (d && d[i]) SVDB_CHECK(c, cudaMemcpyAsync(d[i], dd, sizeof(T) * ni, cudaMemcpyDeviceToHost, lane));
-        if (e && e[i]) SVDB_CHECK(c, cudaMemcpyAsync(e[i], ee, sizeof(T) * (ni - 1), cudaMemcpyDeviceToHost, lane));
-        SVDB_CHECK(c, cudaEventRecord(ev_free[k], lane));
+        res[k] = Result{a[i], d ? d[i] : nullptr, e ? e[i] : nullptr, ni, lane, true};
+        const bool defer = is_pageable(a[i]) || is_pageable(res[k].d) || is_pageable(res[k].e);
+        if (!defer && (st = copy_back(k)) != 0) break;
     }
+    for (int j = 0; j < NB && st == 0; ++j) st = copy_back((int)((count + (size_t)j) % (size_t)NB));   // oldest first
     int sj = drain_into(c, s0);
     cudaError_t es = cudaStreamSynchronize(s0);                       // host buffers are valid on return
     for (auto& ev : ev_free) cudaEventDestroy(ev);

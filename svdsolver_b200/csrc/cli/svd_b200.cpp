@@ -1,7 +1,7 @@
 // svd_b200 -- command-line driver with the reference's CLI contract (svd_cuda_2.cu:1267-1447,
 // README.md:77-119), on top of include/svdb200_matrix.hpp + libsvdb200.so.
 //
-//   svd_b200 benchmark <step> <nsteps> <ninst> <band> [float|double] [stage1|bidiag|svd]
+//   svd_b200 benchmark <step> <nsteps> <ninst> <band> [float|double] [stage1|bidiag|bidiag-many|svd]
 //       positional arguments in the order the reference CODE reads them (svd_cuda_2.cu:1365-1371);
 //       stdout "N = <n> | <sec> sec" per size; two-line CSV (sizes, seconds) in
 //       data/b200_benchmark.csv like data/cuda_2_benchmark.csv; additive extra columns on stdout:
@@ -27,7 +27,7 @@ namespace {
 void print_help() {
     std::cout << "Options for B200 SVD testing" << std::endl;
     std::cout << "\n(1) Run benchmark tests for the band / bidiagonal reduction." << std::endl;
-    std::cout << "\t>> benchmark [<int> Step size] [<int> Number of steps] [<int> Number of test instances] [<int> Band size] [float|double] [stage1|bidiag|svd]";
+    std::cout << "\t>> benchmark [<int> Step size] [<int> Number of steps] [<int> Number of test instances] [<int> Band size] [float|double] [stage1|bidiag|bidiag-many|svd]";
     std::cout << "\n\tExample: ./svd_b200 benchmark 320 12 1 32" << std::endl;
     std::cout << "\n(2) Correctness Test: compares test matrix and corresponding band and bidiagonal reductions" << std::endl;
     std::cout << "\t>> check [64|512|1024 Row/Column sizes] [data dir] [float|double]" << std::endl;
@@ -88,6 +88,19 @@ int run_check(const std::string& nstr, const std::string& dir, const char* tname
     brd_check.print(10);
     std::cout << "\n\nMSE of Bidiagonal Reduction: " << A_tile.mse(brd_check, 2)
               << "   signed rel diff over diagonals 0..1: " << band_rel(A_tile, brd_check, 1) << std::endl;
+    {   // the list entry point against one call per instance (panel order)
+        std::vector<csc586::gpu::Matrix<T>> many{A, A, A};
+        auto Bm = csc586::gpu::cuda_bidiagonalize_many<T>(many, band_size);
+        auto A_one = A;
+        csc586::gpu::cuda_brd_p1(A_one, band_size);
+        auto B1 = csc586::parallel::brd_p2(A_one, band_size);
+        double md = 0;
+        for (auto& Bi : Bm) {
+            for (size_t i = 0; i < B1.d.size(); ++i) md = std::max(md, std::abs((double)Bi.d[i] - (double)B1.d[i]));
+            for (size_t i = 0; i < B1.e.size(); ++i) md = std::max(md, std::abs((double)Bi.e[i] - (double)B1.e[i]));
+        }
+        std::cout << "Max |diff| cuda_bidiagonalize_many vs one call per instance: " << md << std::endl;
+    }
     auto sig = csc586::serial::qrd(B);
     std::cout << "Largest / smallest singular value (QR diagonalisation): " << sig.d.front() << " / " << sig.d.back() << std::endl;
     return 0;
@@ -103,7 +116,7 @@ int run_benchmark(int argc, char* argv[], const std::string& what) {
     (void)argc;
     std::vector<int> x;
     std::vector<float> y;
-    std::cout << "Benchmark: B200 " << (what == "stage1" ? "Band Reduction" : what == "bidiag" ? "Bidiagonal Reduction" : "Singular Values") << std::endl;
+    std::cout << "Benchmark: B200 " << (what == "stage1" ? "Band Reduction" : what == "bidiag" ? "Bidiagonal Reduction" : what == "bidiag-many" ? "Bidiagonal Reduction (instances handed over together)" : "Singular Values") << std::endl;
     std::cout << "\tBand size: " << b_size << std::endl;
     std::cout << "\tStep size: " << step << std::endl;
     std::cout << "\tNumber of steps: " << nsteps - 1 << std::endl;
@@ -115,9 +128,11 @@ int run_benchmark(int argc, char* argv[], const std::string& what) {
         auto B = csc586::parallel::brd_p2<T>(a, b);
         return csc586::serial::qrd<T>(B);
     };
-    {   // warm-up: context + workspace creation are not part of the per-instance time
-        auto w = generate<T>(step, step, 1, min_val, max_val);
+    {   // warm-up: context + workspace creation (sized for the largest matrix of the run) are not part of the per-instance time
+        auto w = generate<T>(step, step, 2, min_val, max_val);
+        csc586::b200::session<T>().get((nsteps - 1) * step, b_size, csc586::b200::dtype_code<T>());
         brd_p1(w[0], b_size);
+        if (what == "bidiag-many") csc586::gpu::cuda_bidiagonalize_many<T>(w, b_size);
     }
     std::cout << "Average time per B200 reduction" << std::endl;
     for (size_t k = 1; k < nsteps; ++k) {
@@ -126,6 +141,7 @@ int run_benchmark(int argc, char* argv[], const std::string& what) {
         float avg = 0;
         if (what == "stage1") avg = csc586::benchmark::benchmark(brd_p1, data, b_size);
         else if (what == "bidiag") avg = csc586::benchmark::benchmark(bidiag, data, b_size);
+        else if (what == "bidiag-many") avg = csc586::benchmark::benchmark_many(csc586::gpu::cuda_bidiagonalize_many<T>, data, b_size);
         else avg = csc586::benchmark::benchmark(svd, data, b_size);
         const double sec = avg * 1e-6;
         std::cout << "N = " << cols << " | " << sec << " sec"

@@ -295,6 +295,25 @@ def test_cli_check_mode(capi, tname):
     assert mse_tile == 0.0 and mse_bid == 0.0          # bit-exact against band_* / bidiagonal_*
     mse_panel = float(re.search(r"MSE of Band Reduction: ([0-9.eE+-]+)", txt).group(1))
     assert mse_panel < (1e-3 if tname == "float" else 1e-9)
+    many = float(re.search(r"cuda_bidiagonalize_many vs one call per instance: ([0-9.eE+-]+)", txt).group(1))
+    assert many == 0.0
+
+
+@pytest.mark.parametrize("what", ["bidiag", "bidiag-many"])
+def test_cli_benchmark_mode(capi, what, tmp_path):
+    """The reference's `benchmark` mode (svd_cuda_2.cu:1350-1405): prints one "N = <n> | <sec> sec" line per size."""
+    import subprocess, re
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "svdsolver_b200", "bin", "svd_b200")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    (tmp_path / "data").mkdir()
+    out = subprocess.run([exe, "benchmark", "128", "2", "3", "32", "double", what], capture_output=True, text=True,
+                         timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr
+    sizes = [int(x) for x in re.findall(r"N = (\d+) \|", out.stdout)]
+    assert sizes == [128, 256]
+    assert (tmp_path / "data" / "b200_benchmark.csv").exists()
 
 
 # ------------------------------------------------------------------ batched (config 5 shape) --------
@@ -445,7 +464,14 @@ def test_bidiagonalize_many_matches_single_calls(capi, oracle, suf, schedule):
         hd = [torch.zeros(n, dtype=tdt).pin_memory() for n in sizes]
         he = [torch.zeros(n, dtype=tdt).pin_memory() for n in sizes]
         h.bidiagonalize_many_inplace([x.data_ptr() for x in host], sizes, b, [x.data_ptr() for x in hd], [x.data_ptr() for x in he])
+        # host variant with PAGEABLE buffers (what std::vector-backed matrices are): copies back are deferred, same bits
+        pg = [np.ascontiguousarray(m.copy()) for m in mats]
+        pd = [np.zeros(n, DT[suf]) for n in sizes]
+        pe = [np.zeros(n, DT[suf]) for n in sizes]
+        h.bidiagonalize_many_inplace([x.ctypes.data for x in pg], sizes, b, [x.ctypes.data for x in pd], [x.ctypes.data for x in pe])
     for i, n in enumerate(sizes):
+        assert np.array_equal(pg[i], host[i].numpy()) and np.array_equal(pd[i], hd[i].numpy())
+        assert np.array_equal(pe[i][:n - 1], he[i].numpy()[:n - 1])
         _, d1, e1 = singles[i]
         scale = float(np.abs(d1).max())
         # Stage 1 rounds differently beside a stage-2 kernel (fixed slices in double).  The reference's stage-2 schedule
