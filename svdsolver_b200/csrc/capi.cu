@@ -636,6 +636,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (pl && pl[0] == '1') c->pipe_light = 1;
         const char* s2l = getenv("SVDB200_S2_LIGHT");
         if (s2l && s2l[0] == '1') c->stage2_light = 1;
+        const char* s2c = getenv("SVDB200_S2_CONST");
+        if (s2c && s2c[0] == '0') c->stage2_const_band = 0;
         const char* prm = getenv("SVDB200_PANEL_REG_MIN");
         if (prm && prm[0]) c->panel_reg_min = atoi(prm);
     }

@@ -79,6 +79,7 @@ struct Ctx {
     void* de2 = nullptr;
     int stage2_light = 0;                   // single matrix: use the 85-register stage-2 variant (3 CTAs per SM) -- pipelined driver
     int stage2_complete = 0;                // 0: the reference's window schedule (parity), 1: complete chase
+    int stage2_const_band = 1;          // band-specialised stage-2 kernels for band 32 / 64 (env SVDB200_S2_CONST=0: generic)
     int qr_method = 0;
     size_t qr_auto_limit = 1024;
     void* bis_ws = nullptr;

@@ -114,7 +114,10 @@ __device__ __forceinline__ void build_h(const T* x, int xs, int L, const T* sc, 
 
 // out(nr x nc) = X(nr x L) * Y(L x nc), k ascending from +0, unfused (matrix.h:243-246).
 // Every finished element is handed to sink(r, cc, value).
-template <typename T, typename Sink>
+// kL > 0: the band is a compile-time constant (leading dimensions too) and interior windows have L == kL -- that case runs
+// a fully unrolled loop whose shared-memory operands are base + immediate (the generic loop spends a third of its issue
+// slots on address arithmetic, prof_r1_s2c).  Same products, same order, same rounding.
+template <typename T, int kL, typename Sink>
 __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, int ldy, int nr, int nc, int L, int CT, int RT,
                                                Sink sink) {
     const int tid = threadIdx.x;
@@ -129,31 +132,57 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
 #pragma unroll
     for (int q = 0; q < kTileR; ++q) xr[q] = min(ry + q * RT, nr - 1) * ldx;
     const int y0 = min(cx, nc - 1), y1 = min(cx + CT, nc - 1);
-    int k = 0;
-    for (; k + 4 <= L; k += 4) {               // operands of 4 steps are fetched before they are consumed
-        T yv[4][2], xv[4][kTileR];
+    if (kL > 0 && L == kL) {
+        const T* Y0 = Y + y0;
+        const T* Y1 = Y + y1;
+        const T* Xq[kTileR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            yv[u][0] = Y[(k + u) * ldy + y0];
-            yv[u][1] = Y[(k + u) * ldy + y1];
+        for (int q = 0; q < kTileR; ++q) Xq[q] = X + xr[q];
 #pragma unroll
-            for (int q = 0; q < kTileR; ++q) xv[u][q] = X[xr[q] + k + u];
+        for (int k = 0; k < (kL > 0 ? kL : 1); k += 4) {
+            T yv[4][2], xv[4][kTileR];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                yv[u][0] = Y0[(k + u) * ldy];
+                yv[u][1] = Y1[(k + u) * ldy];
+#pragma unroll
+                for (int q = 0; q < kTileR; ++q) xv[u][q] = Xq[q][k + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < kTileR; ++q) {
+                    acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
+                    acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
+                }
         }
+    } else {
+        int k = 0;
+        for (; k + 4 <= L; k += 4) {               // operands of 4 steps are fetched before they are consumed
+            T yv[4][2], xv[4][kTileR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) {
+                yv[u][0] = Y[(k + u) * ldy + y0];
+                yv[u][1] = Y[(k + u) * ldy + y1];
+#pragma unroll
+                for (int q = 0; q < kTileR; ++q) xv[u][q] = X[xr[q] + k + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < kTileR; ++q) {
+                    acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
+                    acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
+                }
+        }
+        for (; k < L; ++k) {
+            const T yv0 = Y[k * ldy + y0], yv1 = Y[k * ldy + y1];
 #pragma unroll
             for (int q = 0; q < kTileR; ++q) {
-                acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
-                acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
+                const T xv = X[xr[q] + k];
+                acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv, yv0));
+                acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv, yv1));
             }
-    }
-    for (; k < L; ++k) {
-        const T yv0 = Y[k * ldy + y0], yv1 = Y[k * ldy + y1];
-#pragma unroll
-        for (int q = 0; q < kTileR; ++q) {
-            const T xv = X[xr[q] + k];
-            acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv, yv0));
-            acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv, yv1));
         }
     }
 #pragma unroll
@@ -166,11 +195,12 @@ __device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, 
     }
 }
 
-template <typename T, int kMaxThreads, int kMinBlocks>
+// kC: the band as a compile-time constant (32 / 64: the sizes the configs use), 0 = any band at run time
+template <typename T, int kMaxThreads, int kMinBlocks, int kC>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T* __restrict__ A0, int n, int band, int* __restrict__ prog0,
                                                                       int count, int G, int complete) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = band, w = band + 1;
+    const int c = kC > 0 ? kC : band, w = c + 1;
     const int ldr = c + 1, ldl = 2 * c + 1, ldh = c + 1;
     T* WR = reinterpret_cast<T*>(smem_raw);     // RIGHT window [2c][c+1]
     T* WL = WR + 2 * c * ldr;                   // LEFT  window [c][2c+1]
@@ -243,7 +273,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                 S2_TICK(5);
                 // rows [r0,r1) are finished for this sweep; rows [r1,r2) become LEFT(p)'s left block
                 const int keep = r1 - r0;
-                window_product<T>(WR, ldr, H, ldh, nr, nc, nc, (c + 1) / 2, (c + 1) / 2,
+                window_product<T, kC>(WR, ldr, H, ldh, nr, nc, nc, (c + 1) / 2, (c + 1) / 2,
                                   [&](int r, int cc, T v) {
                                       if (r < keep) st_cg(&A[(size_t)(r0 + r) * N + (r1 + cc)], v);
                                       else WL[(r - keep) * ldl + cc] = v;
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                 }
                 __syncthreads();
                 // cols [r1,r2) are finished; cols [r2,c3) become the top block of RIGHT(p+1)
-                window_product<T>(H, ldh, WL, ldl, nr, nc, nr, c, (c + 3) / 4,
+                window_product<T, kC>(H, ldh, WL, ldl, nr, nc, nr, c, (c + 3) / 4,
                                   [&](int r, int cc, T v) {
                                       if (cc < fc || !fwd) st_cg(&A[(size_t)(r1 + r) * N + (r1 + cc)], v);
                                       else WR[r * ldr + (cc - fc)] = v;
@@ -331,8 +361,13 @@ int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int co
     if (smem > 227 * 1024) return SVDB200_E_CAPACITY;
     // small bands run with <= 256 threads: instantiate that case without the 64-register cap; a batch wants
     // several CTAs per SM instead (the window product is FP64-issue bound for ~40 % of an op, the rest is latency)
-    auto kern = nt <= 256 ? ((count > 1 || c->stage2_light) ? stage2_chase_kernel<T, 256, 3> : stage2_chase_kernel<T, 256, 1>)
-                          : stage2_chase_kernel<T, 1024, 1>;
+    const bool light = count > 1 || c->stage2_light;
+    auto kern = nt <= 256 ? (light ? stage2_chase_kernel<T, 256, 3, 0> : stage2_chase_kernel<T, 256, 1, 0>)
+                          : stage2_chase_kernel<T, 1024, 1, 0>;
+    if (c->stage2_const_band) {                                      // band-specialised instances (same arithmetic)
+        if (cb == 32) kern = light ? stage2_chase_kernel<T, 256, 3, 32> : stage2_chase_kernel<T, 256, 1, 32>;
+        else if (cb == 64) kern = stage2_chase_kernel<T, 1024, 1, 64>;
+    }
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVDB_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
