@@ -44,7 +44,7 @@ UNIT = "GFLOP/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one stage2_chase_kernel<double> launch at n = 3840, band 32 from the
 # committed ncu --set full capture (profiles/); None until measured
-S2_TRAFFIC = 4479488   # 3.477 MB read + 1.002 MB written (profiles/r01_summary.md, prof_r1_s2c)
+S2_TRAFFIC = 4612608   # 3.450 MB read + 1.162 MB written (profiles/r01_summary.md, prof_r1_s2d: n = 3840, band 32, f64)
 
 
 def flops(n):
