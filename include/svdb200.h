@@ -129,6 +129,16 @@ int svdb200_svdvals_batched_f64(svdb200_handle h, double* a, size_t count, size_
 int svdb200_svdvals_batched_dev_f32(svdb200_handle h, float* a_dev, size_t count, size_t n, size_t band, float* sigma_dev);
 int svdb200_svdvals_batched_dev_f64(svdb200_handle h, double* a_dev, size_t count, size_t n, size_t band, double* sigma_dev);
 
+/* The stages of the batched path one at a time (parity tests gate the band and the bidiagonal separately): what is a
+ * bit mask, 1 = stage 1 (a: dense -> band), 2 = stage 2 (a: band -> bidiagonal; d / e, count x n each, optional),
+ * 4 = singular values (of the bidiagonals just computed, or of caller-provided d / e when bit 2 is clear).
+ * n <= 1024, band <= 64 (the range of the one-launch-per-step batched kernels). */
+int svdb200_chain_batched_dev_f32(svdb200_handle h, float* a_dev, size_t count, size_t n, size_t band, int what, float* d_dev, float* e_dev, float* sigma_dev);
+int svdb200_chain_batched_dev_f64(svdb200_handle h, double* a_dev, size_t count, size_t n, size_t band, int what, double* d_dev, double* e_dev, double* sigma_dev);
+/* Test hook for svdb200_bidiagonalize_many_*: dev_bufs[i] (device, n[i] x n[i] elements, or NULL) receives the band
+ * matrix with which matrix i of the NEXT many-call enters stage 2; cleared by that call. */
+int svdb200_set_band_capture(svdb200_handle h, void* const* dev_bufs, size_t count);
+
 /* ---- Measurement helpers ------------------------------------------------------------------------
  * Device time (CUDA events on the handle's stream) of the stages of the LAST host-pointer call, ms.
  * stage-1 sub-times: panel factorisations vs trailing updates are reported by svdb200_stage1_profile. */

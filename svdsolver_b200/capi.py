@@ -214,6 +214,14 @@ class Handle:
     def svdvals_batched_dev(self, a_ptr, count, n, band, sigma_ptr):
         self._check(self._fn("svdvals_batched_dev")(self.h, _p(a_ptr), Z(count), Z(n), Z(band), _p(sigma_ptr)))
 
+    def chain_batched_dev(self, a_ptr, count, n, band, what, d_ptr=None, e_ptr=None, sigma_ptr=None):
+        """stages of the batched path: what = 1 stage 1 | 2 stage 2 | 4 singular values"""
+        self._check(self._fn("chain_batched_dev")(self.h, _p(a_ptr), Z(count), Z(n), Z(band), ctypes.c_int(what), _p(d_ptr), _p(e_ptr), _p(sigma_ptr)))
+
+    def set_band_capture(self, dev_ptrs):
+        """test hook: device buffers that receive the band of matrix i of the next bidiagonalize_many_* call"""
+        self._check(lib().svdb200_set_band_capture(self.h, self._ptr_arrays(dev_ptrs), Z(len(dev_ptrs))))
+
     def fill_uniform_dev(self, a_ptr, count, seed, lo=0.0, hi=5.0):
         self._check(self._fn("fill_uniform_dev")(self.h, _p(a_ptr), Z(count), ctypes.c_ulonglong(seed), ctypes.c_double(lo), ctypes.c_double(hi)))
 

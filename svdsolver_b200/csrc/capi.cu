@@ -183,13 +183,23 @@ int probe_peak(Ctx* c, int kind, double* tflops) {
 // Shards by matrix across GPUs at the caller's level (one handle per GPU), no collective.
 constexpr int kBatchPool = 16;
 
+// Sub-handles (batch pool, stage-1 chains of the pipelined driver) follow the parent's run-time switches on every call,
+// not only those set after the sub-handle was created.
+static void inherit_settings(const Ctx* c, Ctx* s) {
+    s->stage2_complete = c->stage2_complete; s->stage2_const_band = c->stage2_const_band;
+    s->qr_method = c->qr_method; s->qr_auto_limit = c->qr_auto_limit;
+    s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems;
+    s->lookahead = c->lookahead; s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
+    s->panel_tsqr = c->panel_tsqr;
+}
+
 // Small matrices (n <= 1024, band <= 64): every kernel of the path runs ONCE PER STEP FOR THE WHOLE BATCH -- a
 // thread-block cluster per matrix for the panels (panel resident in cluster shared memory), one grid slice per
 // matrix for the three update GEMMs, groups of CTAs that pipeline the sweeps of one matrix each for stage 2, one
 // thread per singular value for the bisection -- instead of ~80 launches per matrix.  The matrices of a chunk stay
 // L2 / HBM resident; workspace is (5 n b + 2 n) elements per matrix of the chunk.
 template <typename T>
-int batched_small(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
+int batched_small(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma, int what = 7, T* d_out = nullptr, T* e_out = nullptr) {
     const int b = (int)band;
     const size_t per_mat = 5 * n * band + 2 * n;
     size_t chunk = std::min<size_t>(count, 8192);
@@ -212,7 +222,7 @@ int batched_small(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
     for (size_t z0 = 0; z0 < count; z0 += chunk) {
         const int cnt = (int)std::min(chunk, count - z0);
         T* a0 = a + z0 * sA;
-        for (size_t k = 0; k < n; k += band) {           // same panel sequence as stage1_panel_order (svd_cpu.h:382-423)
+        for (size_t k = 0; (what & 1) && k < n; k += band) {   // same panel sequence as stage1_panel_order (svd_cpu.h:382-423)
             const int m = (int)(n - k), nc = (int)(n - k - band);
             const bool has_lq = (k + band < n - 1);
             SVDB_TRY((panel_batched<T, false>(c, a0 + k * n + k, n, sA, m, b, Vq, V2q, sV, cnt)));
@@ -231,7 +241,17 @@ int batched_small(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma) {
                 }
             }
         }
-        SVDB_TRY(stage2_chase_batched<T>(c, a0, n, band, dall, eall, cnt));
+        if (what & 2) {
+            SVDB_TRY(stage2_chase_batched<T>(c, a0, n, band, dall, eall, cnt));
+            if (d_out) SVDB_CHECK(c, cudaMemcpyAsync(d_out + z0 * n, dall, sizeof(T) * n * cnt, cudaMemcpyDeviceToDevice, c->stream));
+            if (e_out) SVDB_CHECK(c, cudaMemcpyAsync(e_out + z0 * n, eall, sizeof(T) * n * cnt, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (!(what & 4)) continue;
+        if (!(what & 2)) {                                // sigma of caller-provided bidiagonals
+            if (!d_out || !e_out) return SVDB200_E_ARG;
+            SVDB_CHECK(c, cudaMemcpyAsync(dall, d_out + z0 * n, sizeof(T) * n * cnt, cudaMemcpyDeviceToDevice, c->stream));
+            SVDB_CHECK(c, cudaMemcpyAsync(eall, e_out + z0 * n, sizeof(T) * n * cnt, cudaMemcpyDeviceToDevice, c->stream));
+        }
         if (c->qr_method == 1) {                          // the reference's zero-shift QR sweeps, one CTA per matrix
             for (int i = 0; i < cnt; ++i) SVDB_TRY(bidiag_qr<T>(c, dall + (size_t)i * n, eall + (size_t)i * n, n, sigma + (z0 + i) * n));
         } else {
@@ -259,16 +279,24 @@ int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma)
         }
         c->pool_n = n; c->pool_band = band;
     }
-    const int K = (int)std::min<size_t>(c->pool.size(), count);
+    // Several matrices in flight: stage 1 may then only use kernels without cross-cluster / grid-wide spin waits (their
+    // CTAs must all be co-resident, which the neighbours' panels and cooperative stage-2 grids could prevent:
+    // stage1_panel_reg.cu).  Matrices whose panels need those kernels (n > kOverlapMaxN) go one after the other instead.
+    const bool concurrent = n <= 4096;
+    const int K = concurrent ? (int)std::min<size_t>(c->pool.size(), count) : 1;
     SVDB_CHECK(c, cudaEventRecord(c->lev[0], c->stream));            // inputs are ready on the caller's stream
     for (int i = 0; i < K; ++i) SVDB_CHECK(c, cudaStreamWaitEvent(c->pool[i]->stream, c->lev[0], 0));
     for (size_t i = 0; i < count; ++i) {
         Ctx* s = c->pool[i % K];
+        inherit_settings(c, s);
         T* ai = a + i * n * n;
         T* d = reinterpret_cast<T*>(s->d);
         T* e = reinterpret_cast<T*>(s->e);
         const long long before = s->launches;
-        SVDB_TRY(stage1_panel_order<T>(s, ai, n, band));
+        s->overlap_safe = (concurrent && K > 1) ? 1 : 0;
+        const int st1 = stage1_panel_order<T>(s, ai, n, band);
+        s->overlap_safe = 0;
+        if (st1 != 0) { c->last_error = s->last_error; return st1; }
         SVDB_TRY(stage2_chase<T>(s, ai, n, band, d, e));
         SVDB_TRY(bidiag_qr<T>(s, d, e, n, sigma + i * n));
         c->launches += s->launches - before;
@@ -279,6 +307,14 @@ int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma)
     }
     return 0;
 }
+template <typename T>
+int batched_chain(Ctx* c, T* a, size_t count, size_t n, size_t band, int what, T* d, T* e, T* sigma) {
+    if (count == 0) return 0;
+    if (!(n <= 1024 && band <= 64 && c->cluster_ok >= 8 && n >= 2)) return SVDB200_E_CAPACITY;
+    return batched_small<T>(c, a, count, n, band, sigma, what, d, e);
+}
+template int batched_chain<float>(Ctx*, float*, size_t, size_t, size_t, int, float*, float*, float*);
+template int batched_chain<double>(Ctx*, double*, size_t, size_t, size_t, int, double*, double*, double*);
 template int batched_svdvals<float>(Ctx*, float*, size_t, size_t, size_t, float*);
 template int batched_svdvals<double>(Ctx*, double*, size_t, size_t, size_t, double*);
 
@@ -292,8 +328,18 @@ template int batched_svdvals<double>(Ctx*, double*, size_t, size_t, size_t, doub
 // for narrower bands the second lane is not used).  Matrices larger than kOverlapMaxN are processed without overlap.
 constexpr size_t kOverlapMaxN = 4096;
 
-static int ensure_s2(Ctx* c) {
-    if (c->s2_stream[0]) return 0;
+static void release_s2(Ctx* c) {
+    for (int l = 0; l < Ctx::kLanes; ++l) {
+        if (c->s1ctx[l]) { svdb200_destroy(reinterpret_cast<svdb200_handle>(c->s1ctx[l])); c->s1ctx[l] = nullptr; }
+        if (l > 0 && c->s2_prog[l]) cudaFree(c->s2_prog[l]);
+        c->s2_prog[l] = nullptr;
+        if (c->s2_stream[l]) { cudaStreamDestroy(c->s2_stream[l]); c->s2_stream[l] = nullptr; }
+    }
+    for (auto& e : c->s2ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    c->s2_ready = 0;
+}
+
+static int ensure_s2_impl(Ctx* c) {
     for (int l = 0; l < Ctx::kLanes; ++l) {
         SVDB_CHECK(c, cudaStreamCreateWithFlags(&c->s2_stream[l], cudaStreamNonBlocking));
         if (l == 0) c->s2_prog[l] = c->prog;
@@ -304,6 +350,16 @@ static int ensure_s2(Ctx* c) {
         c->s1ctx[l] = reinterpret_cast<Ctx*>(h);
     }
     for (auto& e : c->s2ev) SVDB_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+// the pipeline's streams, counters, events and stage-1 sub-handles: all or nothing (a failure half-way is rolled back,
+// so a later call starts from scratch instead of dereferencing what was never created)
+static int ensure_s2(Ctx* c) {
+    if (c->s2_ready) return 0;
+    const int st = ensure_s2_impl(c);
+    if (st != 0) { release_s2(c); return st; }
+    c->s2_ready = 1;
     return 0;
 }
 
@@ -353,6 +409,8 @@ static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, s
         SVDB_TRY(drain_into(c, c->stream));
         if (a_host) SVDB_CHECK(c, cudaMemcpyAsync(a_dev, a_host, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream));
         SVDB_TRY(order == SVDB200_ORDER_PANEL ? stage1_panel_order<T>(c, a_dev, n, band) : stage1_tile_order<T>(c, a_dev, n, band));
+        if (i < c->band_capture.size() && c->band_capture[i])
+            SVDB_CHECK(c, cudaMemcpyAsync(c->band_capture[i], a_dev, sizeof(T) * n * n, cudaMemcpyDeviceToDevice, c->stream));
         SVDB_TRY(stage2_chase<T>(c, a_dev, n, band, d, e));
         SVDB_CHECK(c, cudaEventRecord(c->s2ev[1], c->stream));
         for (int l = 0; l < Ctx::kLanes; ++l) {
@@ -364,14 +422,15 @@ static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, s
     }
     const int k = (int)(i % (size_t)c->lanes);
     Ctx* s = c->s1ctx[k];
-    s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems; s->lookahead = c->lookahead;
-    s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
+    inherit_settings(c, s);
     if (a_host) SVDB_CHECK(c, cudaMemcpyAsync(a_dev, a_host, sizeof(T) * n * n, cudaMemcpyHostToDevice, s->stream));
     s->overlap_safe = 1;
     int st = stage1_panel_order<T>(s, a_dev, n, band);
     s->overlap_safe = 0;
     c->launches += s->launches; s->launches = 0;
     if (st != 0) { c->last_error = s->last_error; return st; }
+    if (i < c->band_capture.size() && c->band_capture[i])            // test hook: the band this matrix enters stage 2 with
+        SVDB_CHECK(c, cudaMemcpyAsync(c->band_capture[i], a_dev, sizeof(T) * n * n, cudaMemcpyDeviceToDevice, s->stream));
     SVDB_CHECK(c, cudaEventRecord(s->lev[0], s->stream));
     SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[k], s->lev[0], 0));
     SVDB_TRY(run_stage2_on_lane<T>(c, k, a_dev, n, band, d, e));
@@ -393,7 +452,9 @@ int bidiagonalize_many_dev(Ctx* c, size_t count, T* const* a, const size_t* n, s
         cudaStream_t lane;
         SVDB_TRY(pipeline_one<T>(c, i, a[i], (const T*)nullptr, n[i], band, order, d ? d[i] : nullptr, e ? e[i] : nullptr, &lane));
     }
-    return drain_into(c, s0);                                         // join
+    const int sj = drain_into(c, s0);                                 // join
+    c->band_capture.clear();
+    return sj;
 }
 template int bidiagonalize_many_dev<float>(Ctx*, size_t, float* const*, const size_t*, size_t, int, float* const*, float* const*);
 template int bidiagonalize_many_dev<double>(Ctx*, size_t, double* const*, const size_t*, size_t, int, double* const*, double* const*);
@@ -423,13 +484,17 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         if (!c->a_stage[k]) SVDB_CHECK(c, cudaMalloc(&c->a_stage[k], c->esz * c->max_n * c->max_n));
     if (!c->de2) SVDB_CHECK(c, cudaMalloc(&c->de2, c->esz * 2 * NBmax * (c->max_n + 8)));
     cudaStream_t s0 = c->stream;
-    cudaEvent_t ev_free[NBmax];                                          // buffer k is free again (its D2H copies have finished)
-    for (auto& ev : ev_free) SVDB_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SVDB_CHECK(c, cudaEventRecord(c->s2ev[0], s0));
     for (int l = 0; l < Ctx::kLanes; ++l) {
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[0], 0));
     }
+    struct EvSet {                                                       // buffer k is free again (its D2H copies have finished)
+        cudaEvent_t ev[NBmax] = {};
+        ~EvSet() { for (auto& x : ev) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t* ev_free = evs.ev;
+    for (auto& ev : evs.ev) SVDB_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     struct Result { T *a, *d, *e; size_t n; cudaStream_t lane; bool live; } res[NBmax] = {};
     auto copy_back = [&](int k) -> int {                              // results of the matrix in staging buffer k -> host
         Result& r = res[k];
@@ -453,8 +518,9 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         T* ee = dd + (c->max_n + 8);
         if ((st = copy_back(k)) != 0) break;                          // a deferred (pageable) result still sitting in this buffer
         if (i >= (size_t)NB) {                                        // the copy into the buffer is issued on the chain's stage-1 stream
-            SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[i % (size_t)c->lanes]->stream, ev_free[k], 0));
-            SVDB_CHECK(c, cudaStreamWaitEvent(s0, ev_free[k], 0));
+            cudaError_t we = cudaStreamWaitEvent(c->s1ctx[i % (size_t)c->lanes]->stream, ev_free[k], 0);
+            if (we == cudaSuccess) we = cudaStreamWaitEvent(s0, ev_free[k], 0);
+            if (we != cudaSuccess) { st = cuda_status(c, we, "cudaStreamWaitEvent"); break; }
         }
         cudaStream_t lane = s0;
         st = pipeline_one<T>(c, i, buf, a[i], ni, band, order, dd, ee, &lane);
@@ -465,8 +531,8 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
     }
     for (int j = 0; j < NB && st == 0; ++j) st = copy_back((int)((count + (size_t)j) % (size_t)NB));   // oldest first
     int sj = drain_into(c, s0);
+    c->band_capture.clear();
     cudaError_t es = cudaStreamSynchronize(s0);                       // host buffers are valid on return
-    for (auto& ev : ev_free) cudaEventDestroy(ev);
     if (st == 0 && sj != 0) return sj;
     if (st == 0 && es != cudaSuccess) return cuda_status(c, es, "cudaStreamSynchronize");
     return st;
@@ -821,6 +887,12 @@ int svdb200_synchronize(svdb200_handle h) {
         if (se != cudaSuccess) return cuda_status(c, se, "batched sync");                                                \
         return 0;                                                                                                        \
     }                                                                                                                    \
+    int svdb200_chain_batched_dev_##S(svdb200_handle h, T* a, size_t count, size_t n, size_t band, int what, T* d, T* e, T* sigma) { \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || what <= 0 || what > 7 || ((what & 4) && !sigma)) return SVDB200_E_ARG;                                 \
+        SVDB_TRY(check_square(c, n, n, band, dtype_of<T>()));                                                            \
+        return batched_chain<T>(c, a, count, n, band, what, d, e, sigma);                                                \
+    }                                                                                                                    \
     int svdb200_mse_##S(svdb200_handle h, const T* a, const T* b, size_t n, size_t band, T* out) {                       \
         SVDB_ENTER(T)                                                                                                    \
         if (!a || !b || !out || n == 0 || band == 0) return SVDB200_E_ARG;                                               \
@@ -867,6 +939,13 @@ int svdb200_last_timings(svdb200_handle h, double* s1, double* s2, double* qr, d
     if (qr) *qr = c->ms_qr;
     if (h2d) *h2d = c->ms_h2d;
     if (d2h) *d2h = c->ms_d2h;
+    return 0;
+}
+
+int svdb200_set_band_capture(svdb200_handle h, void* const* dev_bufs, size_t count) {
+    if (!h || (count && !dev_bufs)) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->band_capture.assign(dev_bufs, dev_bufs + count);
     return 0;
 }
 

@@ -73,6 +73,8 @@ struct Ctx {
     cudaStream_t s2_stream[kLanes] = {};
     int* s2_prog[kLanes] = {};              // progress counters per lane
     cudaEvent_t s2ev[4 + kLanes] = {};
+    int s2_ready = 0;                       // the pipeline's streams / counters / sub-handles below exist (all or nothing)
+    int panel_tsqr = 1;                     // stage-1 panels by TSQR + Householder reconstruction where the shape allows (stage1_tsqr.cu)
     int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
     Ctx* s1ctx[kLanes] = {};                // sub-handles (own workspace + streams): stage 1 of two matrices at a time
     void* a_stage[2 * kLanes] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
@@ -84,6 +86,7 @@ struct Ctx {
     size_t qr_auto_limit = 1024;
     void* bis_ws = nullptr;
     size_t bis_ws_elems = 0;
+    std::vector<void*> band_capture;           // test hook of bidiagonalize_many_*: device buffers that receive matrix i's band
     // batched small-matrix driver: per-matrix progress counters, reflector / W workspaces, d / e rows
     int* batch_prog = nullptr;
     size_t batch_prog_elems = 0;
@@ -211,6 +214,7 @@ template <typename T> int bidiag_bisect_batched(Ctx* c, const T* d, const T* e, 
 template <typename T> int fill_uniform(Ctx* c, T* a, size_t count, unsigned long long seed, double lo, double hi);
 template <typename T> int mse_metric(Ctx* c, const T* a, const T* b, size_t n, size_t band, T* out_host);
 template <typename T> int batched_svdvals(Ctx* c, T* a, size_t count, size_t n, size_t band, T* sigma);
+template <typename T> int batched_chain(Ctx* c, T* a, size_t count, size_t n, size_t band, int what, T* d, T* e, T* sigma);
 int probe_peak(Ctx* c, int kind, double* tflops);
 int probe_tc05_tf32(Ctx* c, double* tflops);
 int panel_reg_debug_read(long long* out16);

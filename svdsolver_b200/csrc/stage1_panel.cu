@@ -430,7 +430,12 @@ int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
                 if (nc > band) SVDB_TRY(rank_update<T>(c, A3 + band, n, mr, nc - band, band, W, V2l + band, nc));
             }
         } else if (nc > 0) {
-            // no LQ for this step (only when the trailing block is a single column): next QR panel directly
+            // no LQ for this step (only when the trailing block is a single column): next QR panel directly,
+            // once the update just enqueued on the main stream has landed
+            if (ahead) {
+                SVDB_CHECK(c, cudaEventRecord(c->lev[2], s0));
+                SVDB_CHECK(c, cudaStreamWaitEvent(s1, c->lev[2], 0));
+            }
             SVDB_TRY((launch_panel<T, false>(c, a + (k + band) * n + k + band, n, (int)(m - band), b, Vq, V2q, s1)));
             if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[1], s1));
         }

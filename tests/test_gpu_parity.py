@@ -335,9 +335,12 @@ def test_batched_svdvals(capi, suf, count, n, b):
     assert np.all(np.diff(sig, axis=1) <= 0)
 
 
-@pytest.mark.parametrize("suf,count,n,b", [("f64", 300, 64, 32), ("f64", 5, 512, 64), ("f32", 40, 256, 32), ("f64", 7, 96, 32)])
+@pytest.mark.parametrize("suf,count,n,b", [("f64", 300, 64, 32), ("f64", 5, 512, 64), ("f64", 7, 96, 32)])
 def test_batched_svdvals_vs_oracle_chain(capi, oracle, suf, count, n, b):
-    """batched path vs the CPU oracle chain (panel-order stage 1 -> stage 2) + LAPACK on the oracle's bidiagonal"""
+    """batched path vs the CPU oracle chain (panel-order stage 1 -> stage 2) + LAPACK on the oracle's bidiagonal.
+    Double only: in float the reference's stage-2 schedule amplifies fp32 rounding differences of stage 1 to the 1e-3
+    level, so the float batched path is gated stage by stage instead (band at 1e-4, stage 2 bit-exact:
+    tests/test_gpu_parity_large.py::test_batched_stages_band_tolerance_and_stage2_bit_exact)."""
     a = np.stack([uniform_matrix(n, n, 1000 + i, 0.0, 5.0, DT[suf]) for i in range(count)])
     with handle(capi, n, b, suf) as h:
         sig = h.svdvals_batched(a, b)
@@ -345,10 +348,7 @@ def test_batched_svdvals_vs_oracle_chain(capi, oracle, suf, count, n, b):
         band = oracle.brd_p1_panel(a[i], b)
         _, d, e = oracle.brd_p2(band, b)
         ref = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
-        # double: gated at the path's tolerance.  float: the reference's stage-2 schedule amplifies fp32 rounding
-        # differences of stage 1 to the 1e-3 level -- its own -O3 build differs from its -O2 build by 1.4e-3 at
-        # n = 512 (chain-level float diffs are reported, not gated at 1e-4) -- so float is gated at 5e-3.
-        tol = TOL[suf] if suf == "f64" else 5e-3
+        tol = TOL[suf]
         assert np.abs(sig[i].astype(np.float64) - ref).max() <= tol * ref[0]
 
 
@@ -431,7 +431,7 @@ def test_svdvals_complete_schedule_matches_lapack(capi, suf, n, b):
     with handle(capi, n, b, suf) as h:
         h.set_stage2_schedule(1)
         sig, _ = h.svdvals(a.copy(), b)
-        sigb = h.svdvals_batched(np.stack([a, a]), b) if n <= 1024 else None
+        sigb = h.svdvals_batched(np.stack([a, a]), b)        # n > 1024: the sub-handle pool follows the handle's schedule
     tol = 2e-5 if suf == "f32" else 1e-11
     assert np.abs(sig.astype(np.float64) - s0).max() <= tol * s0[0]
     if sigb is not None:
