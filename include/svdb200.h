@@ -177,6 +177,10 @@ int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
  * the same windows and arithmetic, continued until they are empty; orthogonally equivalent to the input (sigma to
  * round-off).  Use 0 for parity with the reference, 1 when the singular values themselves matter. */
 int svdb200_set_stage2_schedule(svdb200_handle h, int mode);
+/* Stage-1 panel kernel: 1 (default) = blocked kernel, one exchange between the CTAs per sub-panel of 8 columns
+ * (band a multiple of 8, <= 64); 0 = the per-column kernels (one exchange per column).  Same results to round-off. */
+int svdb200_set_panel_kernel(svdb200_handle h, int blocked);
+int svdb200_debug_panel_blk_timing(long long* out16);
 /* Debug: per-phase cycle counters of the register panel kernel (all zero unless built with -DSVDB_PANEL_TIMING=1). */
 int svdb200_debug_panel_timing(long long* out16);
 /* same for the stage-2 kernel (-DSVDB_S2_TIMING=1): RIGHT ops of CTA 1 */

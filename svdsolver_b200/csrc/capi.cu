@@ -190,7 +190,7 @@ static void inherit_settings(const Ctx* c, Ctx* s) {
     s->qr_method = c->qr_method; s->qr_auto_limit = c->qr_auto_limit;
     s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems;
     s->lookahead = c->lookahead; s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
-    s->panel_tsqr = c->panel_tsqr;
+    s->panel_blk = c->panel_blk;
 }
 
 // Small matrices (n <= 1024, band <= 64): every kernel of the path runs ONCE PER STEP FOR THE WHOLE BATCH -- a
@@ -704,6 +704,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (s2l && s2l[0] == '1') c->stage2_light = 1;
         const char* s2c = getenv("SVDB200_S2_CONST");
         if (s2c && s2c[0] == '0') c->stage2_const_band = 0;
+        const char* pb = getenv("SVDB200_PANEL_BLK");
+        if (pb && pb[0] == '0') c->panel_blk = 0;
         const char* prm = getenv("SVDB200_PANEL_REG_MIN");
         if (prm && prm[0]) c->panel_reg_min = atoi(prm);
     }
@@ -715,6 +717,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     SVDB_CREATE_CHECK(cudaMalloc(&c->tau, es * band));
     SVDB_CREATE_CHECK(cudaMalloc(&c->red, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));
     SVDB_CREATE_CHECK(cudaMemset(c->red, 0, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));   // flag-stamped words start unset
+    SVDB_CREATE_CHECK(cudaMalloc(&c->red2, 512 * 1024));
+    SVDB_CREATE_CHECK(cudaMemset(c->red2, 0, 512 * 1024));
     SVDB_CREATE_CHECK(cudaMalloc(&c->bar, 64));
     SVDB_CREATE_CHECK(cudaMemset(c->bar, 0, 64));
     SVDB_CREATE_CHECK(cudaMalloc(&c->prog, sizeof(int) * (max_n + 8)));
@@ -737,7 +741,7 @@ int svdb200_destroy(svdb200_handle h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
-    void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->bar, c->prog,
+    void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->red2, c->bar, c->prog,
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws, c->de2};
     for (int k = 1; k < 2 * Ctx::kLanes; ++k) if (c->a_stage[k]) cudaFree(c->a_stage[k]);
     for (int l = 0; l < Ctx::kLanes; ++l) if (c->s1ctx[l]) svdb200_destroy(reinterpret_cast<svdb200_handle>(c->s1ctx[l]));
@@ -983,6 +987,12 @@ int svdb200_probe_peak(svdb200_handle h, int kind, double* tflops) {
 
 int svdb200_debug_stage2_timing(long long* out16) { return out16 ? stage2_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
+int svdb200_debug_panel_blk_timing(long long* out16) { return out16 ? panel_blk_debug_read(out16) : SVDB200_E_ARG; }
+int svdb200_set_panel_kernel(svdb200_handle h, int blocked) {
+    if (!h || blocked < 0 || blocked > 1) return SVDB200_E_ARG;
+    reinterpret_cast<Ctx*>(h)->panel_blk = blocked;
+    return 0;
+}
 
 int svdb200_set_stage2_schedule(svdb200_handle h, int mode) {
     if (!h || mode < 0 || mode > 1) return SVDB200_E_ARG;

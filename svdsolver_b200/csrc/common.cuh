@@ -37,6 +37,7 @@ struct Ctx {
     void* tau = nullptr;           // band
     unsigned panel_epoch = 0;      // sequence base of the flag-stamped panel all-reduce words (one per launch)
     void* red = nullptr;           // panel all-reduce scratch: 2 * kMaxPanelCtas * (2*band + 8)
+    void* red2 = nullptr;          // blocked panel kernel: flag-stamped words exchanged between clusters through L2 (512 KB)
     unsigned int* bar = nullptr;   // software grid barrier state (2 words) + misc counters
     int* prog = nullptr;           // stage-2 per-sweep progress counters (max_n)
     void* d = nullptr; void* e = nullptr; void* sigma = nullptr;   // max_n each
@@ -74,7 +75,7 @@ struct Ctx {
     int* s2_prog[kLanes] = {};              // progress counters per lane
     cudaEvent_t s2ev[4 + kLanes] = {};
     int s2_ready = 0;                       // the pipeline's streams / counters / sub-handles below exist (all or nothing)
-    int panel_tsqr = 1;                     // stage-1 panels by TSQR + Householder reconstruction where the shape allows (stage1_tsqr.cu)
+    int panel_blk = 1;                      // blocked panel kernel (one exchange per 8 columns, stage1_panel_blk.cu) where the shape allows
     int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
     Ctx* s1ctx[kLanes] = {};                // sub-handles (own workspace + streams): stage 1 of two matrices at a time
     void* a_stage[2 * kLanes] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
@@ -218,6 +219,7 @@ template <typename T> int batched_chain(Ctx* c, T* a, size_t count, size_t n, si
 int probe_peak(Ctx* c, int kind, double* tflops);
 int probe_tc05_tf32(Ctx* c, double* tflops);
 int panel_reg_debug_read(long long* out16);
+int panel_blk_debug_read(long long* out16);
 int stage2_debug_read(long long* out16);
 int tc05_selftest(Ctx* c, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);
 

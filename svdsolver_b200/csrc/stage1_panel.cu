@@ -32,6 +32,9 @@ namespace svdb200 {
 // register-resident fast path (stage1_panel_reg.cu): 0 = ran, 1 = shape not covered
 template <typename T, bool kTrans>
 int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream, bool cooperative);
+// blocked kernel, one exchange per 8 columns (stage1_panel_blk.cu): same convention
+template <typename T, bool kTrans>
+int launch_panel_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
 
 namespace {
 
@@ -248,6 +251,10 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
     if (!V) V = reinterpret_cast<T*>(c->v);
     if (!V2) V2 = reinterpret_cast<T*>(c->v2);
+    if (c->panel_blk) {
+        int st = launch_panel_blk<T, kTrans>(c, a, lda, m, b, V, V2, stream);
+        if (st != 1) return st;
+    }
     // register-resident kernel for tall panels (grid transport); cluster-sized panels are issue-bound
     // either way and stay on the shared-memory kernel below
     if (c->panel_reg && m > c->panel_reg_min) {
