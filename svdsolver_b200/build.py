@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvdb200.so")
-SOURCES = ["capi.cu", "stage1_panel.cu", "stage1_panel_reg.cu", "stage1_panel_blk.cu", "stage1_tile.cu", "gemm.cu", "gemm_fast.cu", "gemm_tc05.cu", "stage2_chase.cu", "bidiag_qr.cu", "bidiag_bisect.cu", "dist.cu"]
+SOURCES = ["capi.cu", "stage1_panel.cu", "stage1_panel_reg.cu", "stage1_panel_blk.cu", "stage1_tile.cu", "gemm.cu", "gemm_fast.cu", "gemm_tc05.cu", "stage2_chase.cu", "stage2_chase_fast.cu", "bidiag_qr.cu", "bidiag_bisect.cu", "dist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
@@ -30,7 +30,10 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), out=None, only=None):
+    """out / only: instrumented side builds (e.g. -DSVDB_PANEL_TIMING=1) into another file, recompiling only the listed sources"""
+    if out is not None:
+        return _build_variant(out, extra, only or SOURCES)
     if not force and not needs_build():
         return LIB
     objs = []
@@ -54,6 +57,23 @@ def build(force=False, verbose=False, extra=()):
     subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     build_cli()
     return LIB
+
+
+def _build_variant(out, extra, only):
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    objs, procs = [], []
+    for s in SOURCES:
+        if s in only:
+            o = os.path.join(bdir, s.replace(".cu", ".var.o"))
+            procs.append(subprocess.Popen([_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", o]))
+        else:
+            o = os.path.join(bdir, s.replace(".cu", ".o"))
+        objs.append(o)
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed")
+    subprocess.check_call([_nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    return out
 
 
 CLI = os.path.join(HERE, "bin", "svd_b200")

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvdb200.so")
+LIB_PATH = os.environ.get("SVDB200_LIB") or os.path.join(HERE, "libsvdb200.so")   # SVDB200_LIB: an instrumented build (tools/)
 
 F32, F64 = 0, 1
 ORDER_PANEL, ORDER_TILE = 0, 1

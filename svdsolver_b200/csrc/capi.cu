@@ -186,7 +186,7 @@ constexpr int kBatchPool = 16;
 // Sub-handles (batch pool, stage-1 chains of the pipelined driver) follow the parent's run-time switches on every call,
 // not only those set after the sub-handle was created.
 static void inherit_settings(const Ctx* c, Ctx* s) {
-    s->stage2_complete = c->stage2_complete; s->stage2_const_band = c->stage2_const_band;
+    s->stage2_complete = c->stage2_complete; s->stage2_const_band = c->stage2_const_band; s->stage2_fast = c->stage2_fast;
     s->qr_method = c->qr_method; s->qr_auto_limit = c->qr_auto_limit;
     s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems;
     s->lookahead = c->lookahead; s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
@@ -704,6 +704,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (s2l && s2l[0] == '1') c->stage2_light = 1;
         const char* s2c = getenv("SVDB200_S2_CONST");
         if (s2c && s2c[0] == '0') c->stage2_const_band = 0;
+        const char* s2f = getenv("SVDB200_S2_FAST");
+        if (s2f && s2f[0] == '0') c->stage2_fast = 0;
         const char* pb = getenv("SVDB200_PANEL_BLK");
         if (pb && pb[0] == '0') c->panel_blk = 0;
         const char* prm = getenv("SVDB200_PANEL_REG_MIN");

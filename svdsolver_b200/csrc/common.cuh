@@ -82,6 +82,7 @@ struct Ctx {
     void* de2 = nullptr;
     int stage2_light = 0;                   // single matrix: use the 85-register stage-2 variant (3 CTAs per SM) -- pipelined driver
     int stage2_complete = 0;                // 0: the reference's window schedule (parity), 1: complete chase
+    int stage2_fast = 1;                // band 32: helper-warp / split-product kernel (stage2_chase_fast.cu; env SVDB200_S2_FAST=0: off)
     int stage2_const_band = 1;          // band-specialised stage-2 kernels for band 32 / 64 (env SVDB200_S2_CONST=0: generic)
     int qr_method = 0;
     size_t qr_auto_limit = 1024;
@@ -198,6 +199,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsi
 
 // ---- internal entry points (one per .cu) ----------------------------------------------------------
 template <typename T> int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e);
+template <typename T> int stage2_chase_fast(Ctx* c, T* a, size_t n, size_t band, int* prog);   // 0 ran, 1 shape not covered
 template <typename T> int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma);
 template <typename T> int bidiag_bisect(Ctx* c, const T* d, const T* e, size_t n, T* sigma);
 template <typename T> int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band);

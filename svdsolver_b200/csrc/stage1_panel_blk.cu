@@ -412,6 +412,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         j += ceff;
         round += 1;
         BLK_TICK(4);
+        if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[8] += 1;
     }
 
     // ---- epilogue (as panel_reg_kernel) --------------------------------------------------------------------------
@@ -473,6 +474,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             for (int rl = lane; rl < R; rl += 32) V2[(size_t)c * m + (r0 + rl)] = Ps[rl * ld + c];
     }
     BLK_TICK(5);
+    if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[9] += 1;
 }
 
 inline size_t blk_smem_bytes(int rows, int b, size_t esz, const BlkShape& sh, size_t* stage_out) {

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <climits>
 #include "common.cuh"
+#include "stage2_common.cuh"
 
 namespace svdb200 {
 
@@ -37,163 +38,7 @@ __device__ long long g_s2_dbg[16];
         }                                                                   \
     } while (0)
 
-// Thread tiling of one window product C = X * Y (nr x L times L x nc): every thread owns a 4 x 2
-// register tile (rows ry + q*RT, columns cx and cx + CT).  Lanes of a warp run along the columns,
-// so Y loads are conflict-free and X loads are broadcasts; odd leading dimensions keep the (at
-// most two) distinct X rows of a warp in different banks.
-constexpr int kTileR = 4, kTileC = 2, kNewPerThread = 4;
-
-__host__ __device__ inline int stage2_threads(int c) {
-    int ct = (c + 1) / 2;
-    int need = ct * ct;                         // RIGHT: CT = RT = ceil(c/2); LEFT: CT = c, RT = ceil(c/4)
-    int need_left = c * ((c + 3) / 4);
-    if (need_left > need) need = need_left;
-    return ((need + 31) / 32) * 32;
-}
-
-// Wait until the predecessor sweep has completed `need` window ops.  `seen` caches the last value read from its
-// counter: counters only grow, so when the predecessor is already far enough ahead no memory access is needed at all
-// (two L2 round trips per op otherwise).  The poll itself is an acquire load: everything the CTA reads from other
-// CTAs afterwards goes through L2 (ld.global.cg), so the L1 invalidation an acquire implies costs nothing here.
-__device__ __forceinline__ int wait_progress(const int* p, int need, int seen) {
-    if (seen >= need) return seen;
-    int v;
-    unsigned polls = 0;
-    unsigned long long t0 = 0;
-    while ((v = ld_acquire(p)) < need) {
-        __nanosleep(20);
-        if ((++polls & 0xfffu) == 0u) {               // a predecessor that never advances must not hang the GPU: trap after 30 s
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 30000000000ull) __trap();
-        }
-    }
-    return v;
-}
-
-// Sequential, unfused sum of squares in index order (matrix.h:59-62) + Householder scalars.
-// guard (complete schedule only): a zero vector keeps alpha = tau = 0, i.e. H = I, instead of dividing by zero
-template <typename T>
-__device__ __forceinline__ void reflector_scalars(const T* x, int xs, int L, T* sc, bool guard) {
-    T acc = (T)0;
-    int i = 0;
-    for (; i + 8 <= L; i += 8) {               // the loads are independent: let them pipeline
-        T v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = x[(i + u) * xs];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = RN<T>::add(acc, RN<T>::mul(v[u], v[u]));
-    }
-    for (; i < L; ++i) {
-        T v = x[i * xs];
-        acc = RN<T>::add(acc, RN<T>::mul(v, v));
-    }
-    T alpha, tau;
-    if (guard && acc == (T)0) { alpha = (T)0; tau = (T)0; }
-    else householder_scalars<T>(x[0], RN<T>::sqrt(acc), alpha, tau);
-    sc[0] = alpha;
-    sc[1] = tau;
-}
-
-// H = I - tau w w^T exactly as svd_serial.h:199-211 (w_0 = 1, w_i = x_i * alpha).
-template <typename T>
-__device__ __forceinline__ void build_h(const T* x, int xs, int L, const T* sc, T* H, int ldh, int tx, int ty, int tys) {
-    const T alpha = sc[0], mtau = -sc[1];
-    if (tx < L) {
-        const int j = tx;
-        const T wj = (j == 0) ? (T)1 : RN<T>::mul(x[j * xs], alpha);
-        for (int i = ty; i < L; i += tys) {
-            T wi = (i == 0) ? (T)1 : RN<T>::mul(x[i * xs], alpha);
-            T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wi, wj)), mtau);
-            if (i == j) h = RN<T>::add((T)1, h);
-            H[i * ldh + j] = h;
-        }
-    }
-}
-
-// out(nr x nc) = X(nr x L) * Y(L x nc), k ascending from +0, unfused (matrix.h:243-246).
-// Every finished element is handed to sink(r, cc, value).
-// kL > 0: the band is a compile-time constant (leading dimensions too) and interior windows have L == kL -- that case runs
-// a fully unrolled loop whose shared-memory operands are base + immediate (the generic loop spends a third of its issue
-// slots on address arithmetic, prof_r1_s2c).  Same products, same order, same rounding.
-template <typename T, int kL, typename Sink>
-__device__ __forceinline__ void window_product(const T* X, int ldx, const T* Y, int ldy, int nr, int nc, int L, int CT, int RT,
-                                               Sink sink) {
-    const int tid = threadIdx.x;
-    const int cx = tid % CT, ry = tid / CT;
-    if (ry >= RT) return;
-    T acc[kTileR][kTileC];
-#pragma unroll
-    for (int q = 0; q < kTileR; ++q)
-#pragma unroll
-        for (int s2 = 0; s2 < kTileC; ++s2) acc[q][s2] = (T)0;
-    int xr[kTileR];
-#pragma unroll
-    for (int q = 0; q < kTileR; ++q) xr[q] = min(ry + q * RT, nr - 1) * ldx;
-    const int y0 = min(cx, nc - 1), y1 = min(cx + CT, nc - 1);
-    if (kL > 0 && L == kL) {
-        const T* Y0 = Y + y0;
-        const T* Y1 = Y + y1;
-        const T* Xq[kTileR];
-#pragma unroll
-        for (int q = 0; q < kTileR; ++q) Xq[q] = X + xr[q];
-#pragma unroll
-        for (int k = 0; k < (kL > 0 ? kL : 1); k += 4) {
-            T yv[4][2], xv[4][kTileR];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                yv[u][0] = Y0[(k + u) * ldy];
-                yv[u][1] = Y1[(k + u) * ldy];
-#pragma unroll
-                for (int q = 0; q < kTileR; ++q) xv[u][q] = Xq[q][k + u];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int q = 0; q < kTileR; ++q) {
-                    acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
-                    acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
-                }
-        }
-    } else {
-        int k = 0;
-        for (; k + 4 <= L; k += 4) {               // operands of 4 steps are fetched before they are consumed
-            T yv[4][2], xv[4][kTileR];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                yv[u][0] = Y[(k + u) * ldy + y0];
-                yv[u][1] = Y[(k + u) * ldy + y1];
-#pragma unroll
-                for (int q = 0; q < kTileR; ++q) xv[u][q] = X[xr[q] + k + u];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int q = 0; q < kTileR; ++q) {
-                    acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv[u][q], yv[u][0]));
-                    acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv[u][q], yv[u][1]));
-                }
-        }
-        for (; k < L; ++k) {
-            const T yv0 = Y[k * ldy + y0], yv1 = Y[k * ldy + y1];
-#pragma unroll
-            for (int q = 0; q < kTileR; ++q) {
-                const T xv = X[xr[q] + k];
-                acc[q][0] = RN<T>::add(acc[q][0], RN<T>::mul(xv, yv0));
-                acc[q][1] = RN<T>::add(acc[q][1], RN<T>::mul(xv, yv1));
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < kTileR; ++q) {
-        const int r = ry + q * RT;
-        if (r < nr) {
-            if (cx < nc) sink(r, cx, acc[q][0]);
-            if (cx + CT < nc) sink(r, cx + CT, acc[q][1]);
-        }
-    }
-}
+using namespace s2;
 
 // kC: the band as a compile-time constant (32 / 64: the sizes the configs use), 0 = any band at run time
 template <typename T, int kMaxThreads, int kMinBlocks, int kC>
@@ -277,7 +122,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                                   [&](int r, int cc, T v) {
                                       if (r < keep) st_cg(&A[(size_t)(r0 + r) * N + (r1 + cc)], v);
                                       else WL[(r - keep) * ldl + cc] = v;
-                                  });
+                                  }, tid);
                 S2_TICK(6);
                 __syncthreads();
                 S2_TICK(7);
@@ -313,7 +158,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) stage2_chase_kernel(T
                                   [&](int r, int cc, T v) {
                                       if (cc < fc || !fwd) st_cg(&A[(size_t)(r1 + r) * N + (r1 + cc)], v);
                                       else WR[r * ldr + (cc - fc)] = v;
-                                  });
+                                  }, tid);
                 fr = fwd ? nr : 0;
                 __syncthreads();
                 if (tid == rel_tid && fwd) st_release(&prog[i], q + 1);
@@ -394,9 +239,16 @@ int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int co
     }
     SVDB_CHECK(c, cudaMemsetAsync(prog, 0, sizeof(int) * n * (size_t)count, c->stream));
     int ni = (int)n, bi = cb, cnt = count, gi = (int)G, complete = c->stage2_complete;
-    void* args[] = {&a, &ni, &bi, &prog, &cnt, &gi, &complete};
-    SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(nt), args, smem, c->stream));
-    c->launches++;
+    int fast = 1;                                                      // 0 = the latency-optimised band-32 kernel ran
+    if (count == 1 && c->stage2_fast && !light) {
+        fast = stage2_chase_fast<T>(c, a, n, band, prog);
+        if (fast != 0 && fast != 1) return fast;
+    }
+    if (fast != 0) {
+        void* args[] = {&a, &ni, &bi, &prog, &cnt, &gi, &complete};
+        SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(nt), args, smem, c->stream));
+        c->launches++;
+    }
     if (d || e) {
         extract_bidiagonal_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)count), 256, 0, c->stream>>>(a, ni, d, e);
         SVDB_CHECK(c, cudaGetLastError());

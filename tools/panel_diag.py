@@ -36,7 +36,8 @@ def small():
                 set_blk(h, blk)
                 out = h.dense_to_band(a, b, capi.ORDER_PANEL)
             res.append(band_rel(out, ref, b))
-        print(f"small n={n} b={b} {suf}: rel vs oracle blocked {res[0]:.3e}  per-column {res[1]:.3e}", flush=True)
+            res.append(band_rel(np.abs(out), np.abs(ref), b))
+        print(f"small n={n} b={b} {suf}: rel vs oracle blocked {res[0]:.3e} (|.| {res[1]:.3e})  per-column {res[2]:.3e} (|.| {res[3]:.3e})", flush=True)
 
 
 def large():
@@ -66,7 +67,8 @@ def large():
                     p = h.get_profile()["panel"]
                     pstr = f"panels {p['ms']:.1f} ms / {p['launches']}"
         diff = float((outs[0] - outs[1]).abs().max() / outs[1].abs().max())
-        print(f"large n={n} b={b} {suf}: stage1 blocked {times[0]:.1f} ms ({pstr})  per-column {times[1]:.1f} ms   band diff {diff:.3e}", flush=True)
+        adiff = float((outs[0].abs() - outs[1].abs()).abs().max() / outs[1].abs().max())
+        print(f"large n={n} b={b} {suf}: stage1 blocked {times[0]:.1f} ms ({pstr})  per-column {times[1]:.1f} ms   band diff {diff:.3e} (|.| {adiff:.3e})", flush=True)
         del a, outs
         torch.cuda.empty_cache()
 
