@@ -152,7 +152,9 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64,f32", "data": "synthetic",
-        "config": workload_config({"sample": f"bounded: n={per_step_sizes} of the sweep per step (the full sweep takes ~45 min on 8 cores, BASELINE.md 2b)"}),
+        "config": workload_config({"sizes_timed": per_step_sizes,
+                                   "sample": f"bounded: n={per_step_sizes} of the sweep per step (the full sweep takes ~45 min on 8 cores, BASELINE.md 2b); "
+                                             "the GPU arm reports its own numbers on exactly these sizes in cpu_baseline.gpu_same_sample"}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -222,6 +224,57 @@ def north_star_shape(capi, torch, stream, dev, local_rank, dt, peaks, hbm_peak, 
         return {"error": str(ex)}
 
 
+def gpu_same_sample(capi, torch, stream, dev, handles, sample_sizes, tdt, reps=5):
+    """The GPU arm on exactly the sizes the CPU reference leg is timed on (like for like): device-resident and end to end
+    (pinned host buffers, copies inside the timed region), f64 + f32, through the same svdb200_bidiagonalize_many_* calls."""
+    from svdsolver_b200.synth import uniform_matrix
+    out = {"sizes": list(sample_sizes)}
+    fl = sum(flops(n) for n in sample_sizes) * len(DTYPES)
+    mats = {suf: [torch.empty(n, n, device=dev, dtype=tdt[suf]) for n in sample_sizes] for suf, _ in DTYPES}
+    dd = {suf: [torch.empty(n, device=dev, dtype=tdt[suf]) for n in sample_sizes] for suf, _ in DTYPES}
+    ee = {suf: [torch.empty(n, device=dev, dtype=tdt[suf]) for n in sample_sizes] for suf, _ in DTYPES}
+    best = None
+    for rep in range(reps + 1):
+        for suf, _ in DTYPES:
+            for n, a in zip(sample_sizes, mats[suf]):
+                handles[suf].fill_uniform_dev(a.data_ptr(), n * n, 586 + n, 0.0, 5.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for suf, _ in DTYPES:
+            handles[suf].bidiagonalize_many_dev([a.data_ptr() for a in mats[suf]], list(sample_sizes), BAND,
+                                                [x.data_ptr() for x in dd[suf]], [x.data_ptr() for x in ee[suf]])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if rep:
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+    out["device_gflops"] = round(fl / (best * 1e-3) * 1e-9, 2)
+    host = []
+    for n in sample_sizes:
+        for suf, dt in DTYPES:
+            src = torch.from_numpy(uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt))
+            host.append((n, suf, src, torch.empty(n, n, dtype=tdt[suf]).pin_memory(), torch.empty(n, dtype=tdt[suf]).pin_memory(),
+                         torch.empty(n, dtype=tdt[suf]).pin_memory()))
+    best = None
+    for rep in range(reps + 1):
+        for _, _, src, buf, _, _ in host:
+            buf.copy_(src)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for suf, _ in DTYPES:
+            hs = [x for x in host if x[1] == suf]
+            handles[suf].bidiagonalize_many_inplace([x[3].data_ptr() for x in hs], [x[0] for x in hs], BAND,
+                                                    [x[4].data_ptr() for x in hs], [x[5].data_ptr() for x in hs])
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) * 1e3
+        if rep:
+            best = t if best is None else min(best, t)
+    out["e2e_gflops"] = round(fl / (best * 1e-3) * 1e-9, 2)
+    out["timer"] = "device: CUDA events; e2e: host wall clock around the blocking C-ABI calls (timing.h:78-83 convention), best of %d" % reps
+    return out
+
+
 def full_configs(capi, torch, stream, dev, local_rank):
     """BASELINE configs[2] (n=16384 double full SVD, band 64) and one GPU's share of configs[4] (1024 of the 8192 batched
     256x256 double SVDs, band 32): device time per stage, CUDA events on the launching stream."""
@@ -257,30 +310,128 @@ def full_configs(capi, torch, stream, dev, local_rank):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["config3_full_svd"] = {"error": str(ex)}
+    return out
+
+
+def batched_config(capi, torch, dist, stream, dev, local_rank, rank, world, barrier):
+    """BASELINE configs[4]: 8192 x (256x256 double SVD, band 32) sharded by matrix over the ranks (no collective on the data
+    path; the max over ranks is taken for the time)."""
     try:
-        cnt, n, b = 1024, 256, 32
+        total, n, b = 8192, 256, 32
+        cnt = total // world + (1 if rank < total % world else 0)
         h = capi.Handle(n, b, np.float64, device=local_rank)
         h.set_stream(stream.cuda_stream)
         a = torch.empty(cnt, n, n, device=dev, dtype=torch.float64)
-        h.fill_uniform_dev(a.data_ptr(), cnt * n * n, 586, 0.0, 5.0)
-        a0 = a.clone()
         sg = torch.empty(cnt, n, device=dev, dtype=torch.float64)
         best = None
         for rep in range(3):
-            a.copy_(a0)
-            torch.cuda.synchronize()
+            h.fill_uniform_dev(a.data_ptr(), cnt * n * n, 586 + 1000003 * rank, 0.0, 5.0)
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             h.svdvals_batched_dev(a.data_ptr(), cnt, n, b, sg.data_ptr())
             e1.record(stream)
-            torch.cuda.synchronize()
+            barrier()
             t = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
             best = t if best is None else min(best, t)
-        out["config5_batched_share"] = {"workload": "1024 x (256x256 double SVD, band 32) = one GPU's share of BASELINE configs[4] at 8 GPUs",
-                                        "ms": round(best, 1), "matrices_per_s": round(cnt / best * 1e3, 1)}
+        ok = bool(torch.isfinite(sg).all().item()) and bool((sg[:, :-1] >= sg[:, 1:]).all().item())
         h.close()
+        del a, sg
+        torch.cuda.empty_cache()
+        return {"workload": f"8192 x (256x256 double SVD, band 32) sharded by matrix over {world} GPU(s) (BASELINE configs[4])",
+                "matrices_per_rank": total // world, "ms": round(best, 1), "matrices_per_s": round(total / best * 1e3, 1),
+                "sigma_sorted_finite_rank0": ok}
     except Exception as ex:
-        out["config5_batched_share"] = {"error": str(ex)}
+        return {"error": str(ex)}
+
+
+def dist_stage1_config(args, capi, torch, dist, stream, dev, local_rank, rank, world, barrier):
+    """BASELINE configs[3] shape: n x n float dense -> band, band 64, 1-D block-cyclic over the columns of `world` GPUs (NCCL
+    panel broadcast).  Runs for every N including 1; with N > 1 rank 0 afterwards times the same driver on one GPU so that
+    the strong-scaling efficiency is measured inside one run.  In-run invariants: Frobenius norm, zeros below the diagonal,
+    round-off above the band."""
+    from svdsolver_b200 import distributed as D
+    nd, bd = args.dist_n, 64
+    out = {"workload": f"{nd}x{nd} float dense->band, band {bd}, block-cyclic columns over {world} GPU(s) (BASELINE configs[3] shape)",
+           "n": nd, "ranks": world}
+
+    def one(nranks, rk, uid, reps):
+        ncl = D.local_cols(nd, bd, rk, nranks)
+        loc = torch.empty(nd, ncl, device=dev, dtype=torch.float32)
+        hfill = capi.Handle(64, 32, np.float32, device=local_rank)
+        hfill.set_stream(stream.cuda_stream)
+        res = {}
+        with D.DistHandle(nd, bd, np.float32, rk, nranks, uid, device=local_rank) as dh:
+            dh.set_stream(stream.cuda_stream)
+            times = []
+            for rep in range(reps):
+                hfill.fill_uniform_dev(loc.data_ptr(), nd * ncl, 586 + nd + 7919 * rk, 0.0, 5.0)
+                torch.cuda.synchronize()
+                if rep == 0:
+                    fro2 = sum(float((loc[:, c0:c0 + 2048].double() ** 2).sum()) for c0 in range(0, ncl, 2048))
+                if nranks > 1:
+                    barrier()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record(stream)
+                dh.dense_to_band_dev(loc.data_ptr())
+                d1.record(stream)
+                if nranks > 1:
+                    barrier()
+                else:
+                    torch.cuda.synchronize()
+                t = d0.elapsed_time(d1)
+                if nranks > 1:
+                    tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t = float(tt.item())
+                times.append(t)
+            res["launches_rank0"] = dh.launch_count()
+        hfill.close()
+        # invariants on the result of the last repetition
+        gcol = (torch.arange(ncl, device=dev) // bd * nranks + rk) * bd + torch.arange(ncl, device=dev) % bd
+        rows = torch.arange(nd, device=dev)
+        fro2b, below, above, amax = 0.0, 0.0, 0.0, 0.0
+        for c0 in range(0, ncl, 1024):
+            blk = loc[:, c0:c0 + 1024]
+            gc = gcol[c0:c0 + 1024]
+            fro2b += float((blk.double() ** 2).sum())
+            amax = max(amax, float(blk.abs().max()))
+            below = max(below, float((blk.abs() * (rows[:, None] > gc[None, :])).max()))
+            above = max(above, float((blk.abs() * (rows[:, None] < gc[None, :] - bd)).max()))
+        vals = torch.tensor([fro2, fro2b], device=dev, dtype=torch.float64)
+        mx = torch.tensor([below, above, amax], device=dev, dtype=torch.float64)
+        if nranks > 1:
+            dist.all_reduce(vals)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        res["ms"] = round(min(times), 1)
+        res["tflops"] = round(flops(nd) / (min(times) * 1e-3) * 1e-12, 2)
+        res["frob_rel_err"] = abs(float(vals[1]) ** 0.5 - float(vals[0]) ** 0.5) / float(vals[0]) ** 0.5
+        res["max_below_diag"] = float(mx[0])
+        res["max_above_band_rel"] = float(mx[1]) / float(mx[2])
+        del loc
+        torch.cuda.empty_cache()
+        return res
+
+    try:
+        uid = D.exchange_unique_id(rank, world)
+        out.update(one(world, rank, uid, 2))
+        out["collectives"] = "ncclBroadcast([V | V S^T]), ncclAllGather(row panel), ncclAllReduce(W)" if world > 1 else "none (one rank)"
+        if world > 1:
+            t1 = torch.zeros(1, device=dev, dtype=torch.float64)
+            if rank == 0:
+                import ctypes
+                r1 = one(1, 0, (ctypes.c_ubyte * 128)(), 1)
+                t1[0] = r1["ms"]
+                out["one_gpu_ms_same_run"] = r1["ms"]
+            barrier()
+            dist.broadcast(t1, src=0)
+            out["strong_eff_vs_N1"] = round(float(t1.item()) / (world * out["ms"]), 3)
+    except Exception as ex:
+        out["error"] = str(ex)
     return out
 
 
@@ -292,7 +443,7 @@ def main():
     ap.add_argument("--impl", default="svdb200")
     ap.add_argument("--sizes", default="")           # debugging: comma-separated subset of the sweep
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dist-n", type=int, default=32768)  # size of the block-cyclic stage-1 measurement (N>1)
+    ap.add_argument("--dist-n", type=int, default=65536)  # size of the block-cyclic stage-1 measurement (BASELINE configs[3])
     ap.add_argument("--no-big", action="store_true")      # skip the n=16384 trailing-update measurement
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -530,56 +681,71 @@ def main():
     e2e = {"value": world * step_flops * e2e_steps / (tot_ms * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "svdb200_bidiagonalize_many_{f64,f32} (host pointers, pinned; double-buffered copies)"}
 
-    # ---- multi-GPU stage 1 (BASELINE config 4 shape): 1-D block-cyclic columns, NCCL panel broadcast ----
-    dist_out = None
-    if world > 1 and not args.no_big:
+    # ---- like-for-like with the CPU reference leg: the GPU on exactly the sizes the CPU sample uses --------------------
+    cpu_sizes = [320, 640]
+    same = None
+    if rank == 0 and not args.sizes:
         try:
-            from svdsolver_b200 import distributed as D
-            for h in handles.values():
-                h.close()
-            handles = {}
-            del sets, dbuf, ebuf
-            torch.cuda.empty_cache()
-            nd, bd = args.dist_n, 64
-            uid = D.exchange_unique_id(rank, world)
-            ncl = D.local_cols(nd, bd, rank, world)
-            loc = torch.empty(nd, ncl, device=dev, dtype=torch.float32)
-            with D.DistHandle(nd, bd, np.float32, rank, world, uid, device=local_rank) as dh:
-                dh.set_stream(stream.cuda_stream)
-                hfill = capi.Handle(64, 32, np.float32, device=local_rank)
-                hfill.set_stream(stream.cuda_stream)
-                times = []
-                for rep in range(2):
-                    hfill.fill_uniform_dev(loc.data_ptr(), nd * ncl, 586 + nd + 7919 * rank, 0.0, 5.0)
-                    barrier()
-                    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    d0.record(stream)
-                    dh.dense_to_band_dev(loc.data_ptr())
-                    d1.record(stream)
-                    barrier()
-                    t = torch.tensor([d0.elapsed_time(d1)], device=dev, dtype=torch.float64)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    times.append(float(t.item()))
-                hfill.close()
-                tms = min(times)
-                dist_out = {"workload": f"{nd}x{nd} float dense->band, band {bd}, block-cyclic columns over {world} GPUs (BASELINE configs[3] shape)",
-                            "ms": round(tms, 1), "tflops": round(flops(nd) / (tms * 1e-3) * 1e-12, 2), "ranks": world,
-                            "launches_rank0": dh.launch_count(), "collectives": "ncclBroadcast(V|V2), ncclAllGather(row panel), ncclAllReduce(W)"}
-            del loc
+            same = gpu_same_sample(capi, torch, stream, dev, handles, cpu_sizes, tdt)
         except Exception as ex:
-            dist_out = {"error": str(ex)}
+            same = {"error": str(ex)}
+    for h in handles.values():
+        h.close()
+    handles = {}
+    del sets, dbuf, ebuf, dmany, emany, host
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] (batched, sharded by matrix) and configs[3] (block-cyclic stage 1), every N -----------------
+    batched_out = dist_out = None
+    if not args.no_big and not args.sizes:
+        batched_out = batched_config(capi, torch, dist, stream, dev, local_rank, rank, world, barrier)
+        dist_out = dist_stage1_config(args, capi, torch, dist, stream, dev, local_rank, rank, world, barrier)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_sample([320, 640])
+        cpu = cpu_reference_sample(cpu_sizes)
         cpu.pop("detail", None)
+        if same and "device_gflops" in same:
+            same["vs_cpu_device"] = round(same["device_gflops"] / cpu["value"], 1)
+            same["vs_cpu_e2e"] = round(same["e2e_gflops"] / cpu["value"], 1)
+        cpu["gpu_same_sample"] = same
+        cpu["note"] = "like for like = gpu_same_sample vs value (same sizes, same dtypes); the headline `value` is the full sweep, which the CPU cannot finish in minutes"
 
     if rank == 0:
+        peak64, peak32 = peaks.get("dfma_tflops"), peaks.get("ffma_tflops")
+        for dsc in detail:
+            pk = peak64 if dsc["dtype"] == "f64" else peak32
+            if pk:
+                dsc["pct_of_fma_peak"] = round(dsc["gflops"] / (pk * 1e3) * 100.0, 2)
+                dsc["stage1_pct_of_fma_peak"] = round(dsc["stage1_gflops"] / (pk * 1e3) * 100.0, 2)
+        cfg = workload_config({"sizes": sizes, "parallelism": f"replicas x{world}", "reference_arm_sizes": cpu_sizes,
+                               "gpu_on_reference_arm_sizes": same})
+        # numbers of the other BASELINE configs live under `config` (a key the driver's record keeps)
+        ns = {}
+        if big and "error" not in big:
+            ns["stage1_n16384_band64_f64"] = {k: big[k] for k in ("stage1_ms", "stage1_tflops", "trailing_update_tflops",
+                                                                  "trailing_update_frac_of_fp64_dmma_peak", "trailing_update_frac_of_hbm_peak") if k in big}
+            ns["stage1_n16384_band64_f64"]["panel_ms"] = big["classes"]["panel"]["ms"]
+        if big32 and "error" not in big32:
+            ns["stage1_n16384_band64_f32"] = {k: big32[k] for k in ("stage1_ms", "stage1_tflops", "trailing_update_tflops",
+                                                                    "trailing_update_frac_of_hbm_peak", "trailing_update_frac_of_3xtf32_tcgen05_peak") if k in big32}
+            ns["stage1_n16384_band64_f32"]["panel_ms"] = big32["classes"]["panel"]["ms"]
+        if other:
+            ns["config2_full_svd_n16384_f64"] = other.get("config3_full_svd")
+        if batched_out:
+            ns["config4_batched_8192x256"] = batched_out
+        if dist_out:
+            ns["config3_block_cyclic_stage1"] = dist_out
+        if peaks:
+            ns["peaks_measured_tflops"] = {k: round(v, 2) for k, v in peaks.items()}
+        cfg["north_star"] = ns
+        if detail:
+            cfg["sweep_pct_of_fma_peak"] = {f"{dsc['n']}_{dsc['dtype']}": dsc.get("pct_of_fma_peak") for dsc in detail}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64,f32", "data": "synthetic", "config": workload_config({"sizes": sizes, "parallelism": f"replicas x{world}"}),
+            "dtype": "f64,f32", "data": "synthetic", "config": cfg,
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_north_star_f32": roofline_ns, "cpu_baseline": cpu,
             "kernel_classes_f64": prof_out, "north_star_shape": big, "north_star_shape_f32": big32, "other_configs": other, "multi_gpu_stage1": dist_out, "peaks_measured": {k: round(v, 2) for k, v in peaks.items()}, "detail": detail,
         }

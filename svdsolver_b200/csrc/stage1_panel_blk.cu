@@ -57,9 +57,7 @@ __device__ __forceinline__ T pick(const T (&v)[CPL], int u) {
 }
 template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template <typename T> __device__ __forceinline__ T guard_ratio();
-template <> __device__ __forceinline__ float guard_ratio<float>() { return 0.25f; }
-template <> __device__ __forceinline__ double guard_ratio<double>() { return 1.0 / 64.0; }
+__device__ __forceinline__ double guard_ratio(bool is_float) { return is_float ? 0.25 : 1.0 / 64.0; }
 
 struct BlkShape {
     int CS, NC, SL, L;
@@ -72,31 +70,60 @@ __host__ __device__ inline BlkShape blk_shape(int b, int CS, int NC) {
     return s;
 }
 
+// Shared-memory plan (bytes).  The staging area holds the transposed load / epilogue copy of the slice (Ps) outside the
+// column loop and the exchange words + per-warp dot products inside it.
+struct BlkSmem {
+    size_t stage, psum_off, total;
+};
+__host__ __device__ inline BlkSmem blk_smem(int rows, int b, size_t esz, const BlkShape& sh) {
+    const size_t CB = (size_t)kC * b;
+    BlkSmem m;
+    const size_t ps = (size_t)rows * (b + 1) * esz;
+    const size_t exch = (sh.CS * sh.NC > 1) ? sh.exch_bytes : 0;
+    m.psum_off = (exch + 15) & ~(size_t)15;
+    const size_t loop = m.psum_off + (size_t)kWarps * CB * 8;
+    m.stage = ((ps > loop ? ps : loop) + 15) & ~(size_t)15;
+    // doubles: red (L) + topS (CB) + Cs (CB) + srow (b) + fas (b);
+    // elements: Tt (b*b) + Gp (2*b*8) + Zs (b*8) + T22s (64) + taus (b) + Kc + TopF (CB each) + xs (kWarps * 256); ctl
+    m.total = m.stage + (2 * CB + CB + CB + 2 * (size_t)b) * 8 +
+              ((size_t)b * b + 24 * (size_t)b + 64 + b + 2 * CB + (size_t)kWarps * 256) * esz + 64;
+    return m;
+}
+
 template <typename T, bool kTrans, int RPT, int CPL>
 __global__ void __launch_bounds__(kThreads, 1)
 panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, char* __restrict__ gbuf, int NC,
-                 unsigned epoch, size_t stage_bytes) {
+                 unsigned epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int ROWS = RPT * kWarps, C = kC;
+    constexpr int ROWS = RPT * kWarps, C = kC, CH = (RPT < 8 ? RPT : 8);
+    constexpr bool kFloat = sizeof(T) == 4;
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31, w = tid >> 5;
     const int G = gridDim.x, g = blockIdx.x;
     const int CS = G / NC, cl = g / CS, crank = g - cl * CS;
     const BlkShape sh = blk_shape(b, CS, NC);
+    const BlkSmem plan = blk_smem(ROWS, b, sizeof(T), sh);
     const int L = sh.L, SL = sh.SL, CB = C * b;
     const int r0 = g * ROWS;
     const int R = max(0, min(ROWS, m - r0));
     const int ld = b + 1;
     // ---- shared memory ----------------------------------------------------------------------------------
-    unsigned char* stage = smem_raw;                      // Ps (ROWS x ld: transposed load, epilogue) / exchange words (loop)
-    T* Ps = reinterpret_cast<T*>(stage);
-    T* Gm = reinterpret_cast<T*>(stage + stage_bytes);    // b x b : Gm[c][j] = v_c^T v_j (c < j)
-    T* taus = Gm + b * b;                                 // b
-    T* psum = taus + b;                                   // kWarps x CB : per-warp dot products (reused for slice partials)
-    T* topS = psum + kWarps * CB;                         // CB : this CTA's rows among the C top rows (zeros elsewhere)
-    T* red = topS + CB;                                   // L  : reduced D (CB) followed by Top (CB)
-    T* Kc = red + L;                                      // CB : pass coefficients per column
+    unsigned char* stage = smem_raw;
+    T* Ps = reinterpret_cast<T*>(stage);                  // ROWS x ld (outside the column loop)
+    double* psum = reinterpret_cast<double*>(stage + plan.psum_off);   // kWarps x CB (inside the loop; reused for slice partials)
+    double* red = reinterpret_cast<double*>(stage + plan.stage);       // L : reduced D (CB), then Top (CB) -- the algebra works on Top in place
+    double* topS = red + L;                               // CB : this CTA's rows among the C top rows (zeros elsewhere)
+    double* Cs = topS + CB;                               // CB : coefficients Cm[p][col] of the algebra
+    double* srow = Cs + CB;                               // b  : row i of S (dots of the pivot column's lo part with every column)
+    double* fas = srow + b;                               // b  : f_k * alpha of the current step
+    T* Tt = reinterpret_cast<T*>(fas + b);                // b x b : Tt[k*b + c] = T[c][k] (compact-WY T, upper triangular)
+    T* Gp = Tt + b * b;                                   // 2 x (b x 8): v_col^T v_(j+q) of the current / previous sub-panel
+    T* Zs = Gp + 2 * b * 8;                               // b x 8
+    T* T22s = Zs + b * 8;                                 // 8 x 8
+    T* taus = T22s + 64;                                  // b
+    T* Kc = taus + b;                                     // CB : pass coefficients per column
     T* TopF = Kc + CB;                                    // CB : final top rows of the sub-panel
-    int* ctl = reinterpret_cast<int*>(TopF + CB);         // [0] = C_eff
+    T* xs = TopF + CB;                                    // kWarps x 2 (chunk parity) x 2 (x / y) x CH x 8 : broadcast staging
+    int* ctl = reinterpret_cast<int*>(xs + kWarps * 256);  // [0] = C_eff
     const unsigned l1_base = smem_addr(stage);
     const unsigned in_bytes = (unsigned)(2 * CS * SL * 16);
     auto in_off = [&](int par, int src, int e) { return (unsigned)(((par * CS + src) * SL + e) * 16); };
@@ -129,74 +156,194 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             for (int u = 0; u < CPL; ++u) a[i][u] = (rl < R && valid[u]) ? Ps[rl * ld + cu[u]] : (T)0;
         }
     }
-    for (int e = tid; e < b * b; e += nt) Gm[e] = (T)0;
-    for (int e = tid; e < CB; e += nt) topS[e] = (T)0;
     __syncthreads();                                      // the transposed load is done with Ps
+    for (int e = tid; e < b * b; e += nt) Tt[e] = (T)0;
+    for (int e = tid; e < CB; e += nt) topS[e] = 0.0;
     if (G > 1) {
         unsigned* z = reinterpret_cast<unsigned*>(stage);
         for (int e = tid; e < (int)(sh.exch_bytes / 4); e += nt) z[e] = 0u;
         cg::this_cluster().sync();                        // every peer's word buffers are cleared before the first push
+    } else {
+        __syncthreads();
     }
 
     const int kmax = b;                                   // m >= b (checked by the launcher)
-    T acc[C][CPL];
+    double acc[C][CPL];
+    T* xw = xs + w * 256;
     // One pass over the local rows.  apply: update with the coefficients of the sub-panel that started at column j and
-    // processed ceff columns; then (always) dot products and top rows for the sub-panel starting at jn.
+    // processed ceff columns; then (always) dot products and top rows for the sub-panel starting at jn.  The C values of a
+    // row that every lane needs (the sub-panel's columns) travel through a per-warp staging buffer in shared memory
+    // (one predicated store + vector broadcast loads per row instead of 2 C shuffles); the loop body has no branches.
     auto pass = [&](bool apply, int j, int ceff, int jn) {
         T K[C][CPL];
         bool fin[CPL];
+        int pcx[CPL], pcy[CPL];
 #pragma unroll
         for (int u = 0; u < CPL; ++u) {
             fin[u] = apply && cu[u] >= j && cu[u] < j + ceff;
+            pcx[u] = (apply && valid[u] && cu[u] >= j && cu[u] < j + C) ? cu[u] - j : -1;
+            pcy[u] = (valid[u] && cu[u] >= jn && cu[u] < jn + C) ? cu[u] - jn : -1;
 #pragma unroll
             for (int p = 0; p < C; ++p) K[p][u] = (apply && valid[u]) ? Kc[p * b + cu[u]] : (T)0;
         }
 #pragma unroll
         for (int p = 0; p < C; ++p)
 #pragma unroll
-            for (int u = 0; u < CPL; ++u) acc[p][u] = (T)0;
+            for (int u = 0; u < CPL; ++u) acc[p][u] = 0.0;
         const bool more = jn < kmax;
+        // rows that sit among the C top rows of the finished sub-panel take their final values from the algebra
+        if (apply) {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int rl = w + kWarps * i;
-            const int grow = r0 + rl;
-            const bool inb = rl < R;                      // warp-uniform: a warp works on one row at a time
-            if (apply && inb && grow >= j) {
-                if (grow < j + C) {
-                    const int t = grow - j;
+            for (int i = 0; i < RPT; ++i) {
+                const int rl = w + kWarps * i, t = r0 + rl - j;
+                if (rl < R && t >= 0 && t < C) {
 #pragma unroll
                     for (int u = 0; u < CPL; ++u) if (valid[u]) a[i][u] = TopF[t * b + cu[u]];
-                } else {
-                    T x[C];
+                }
+            }
+        }
+        T ymask[C];
 #pragma unroll
-                    for (int p = 0; p < C; ++p) x[p] = bcast(pick<T, CPL>(a[i], (j + p) >> 5), (j + p) & 31);
+        for (int p = 0; p < C; ++p) ymask[p] = (more && jn + p < kmax) ? (T)1 : (T)0;
+#pragma unroll
+        for (int i0 = 0; i0 < RPT; i0 += CH) {
+            T* bx = xw + ((i0 / CH) & 1) * 128;           // chunk parity: a buffer is rewritten two __syncwarp()s after its last read
+            T* by = bx + 64;
+            T x[CH][C];
+            if (apply) {
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii)
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) if (pcx[u] >= 0) bx[ii * 8 + pcx[u]] = a[i0 + ii][u];
+                __syncwarp();
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii) {
+                    if constexpr (kFloat) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(bx + ii * 8), v1 = *reinterpret_cast<const float4*>(bx + ii * 8 + 4);
+                        x[ii][0] = v0.x; x[ii][1] = v0.y; x[ii][2] = v0.z; x[ii][3] = v0.w; x[ii][4] = v1.x; x[ii][5] = v1.y; x[ii][6] = v1.z; x[ii][7] = v1.w;
+                    } else {
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const double2 v = *reinterpret_cast<const double2*>(bx + ii * 8 + 2 * p2);
+                            x[ii][2 * p2] = v.x; x[ii][2 * p2 + 1] = v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii) {
+                    const int i = i0 + ii, rl = w + kWarps * i;
+                    const bool islo = rl < R && (r0 + rl) >= j + C;          // warp-uniform
+                    const T lo = islo ? (T)1 : (T)0;
 #pragma unroll
                     for (int u = 0; u < CPL; ++u) {
-                        T v = fin[u] ? (T)0 : a[i][u];
+                        T v = (islo && fin[u]) ? (T)0 : a[i][u];
 #pragma unroll
-                        for (int p = 0; p < C; ++p) v += x[p] * K[p][u];
+                        for (int p = 0; p < C; ++p) v += (lo * x[ii][p]) * K[p][u];
                         a[i][u] = v;
                     }
                 }
             }
-            if (more && inb && grow >= jn) {
-                if (grow < jn + C) {
-                    const int t = grow - jn;
+            if (more) {
 #pragma unroll
-                    for (int u = 0; u < CPL; ++u) if (valid[u]) topS[t * b + cu[u]] = a[i][u];
-                } else {
+                for (int ii = 0; ii < CH; ++ii)
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) if (pcy[u] >= 0) by[ii * 8 + pcy[u]] = a[i0 + ii][u];
+                __syncwarp();
+                T accf[C][CPL];
+#pragma unroll
+                for (int p = 0; p < C; ++p)
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) accf[p][u] = (T)0;
+#pragma unroll
+                for (int ii = 0; ii < CH; ++ii) {
                     T y[C];
+                    if constexpr (kFloat) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(by + ii * 8), v1 = *reinterpret_cast<const float4*>(by + ii * 8 + 4);
+                        y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; y[5] = v1.y; y[6] = v1.z; y[7] = v1.w;
+                    } else {
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const double2 v = *reinterpret_cast<const double2*>(by + ii * 8 + 2 * p2);
+                            y[2 * p2] = v.x; y[2 * p2 + 1] = v.y;
+                        }
+                    }
+                    const int i = i0 + ii, rl = w + kWarps * i;
+                    const T lo2 = (rl < R && (r0 + rl) >= jn + C) ? (T)1 : (T)0;
 #pragma unroll
                     for (int p = 0; p < C; ++p) {
-                        const T yv = bcast(pick<T, CPL>(a[i], (jn + p) >> 5), (jn + p) & 31);
-                        y[p] = (jn + p < kmax) ? yv : (T)0;
+                        const T yv = y[p] * (lo2 * ymask[p]);
+#pragma unroll
+                        for (int u = 0; u < CPL; ++u) accf[p][u] += yv * a[i][u];
                     }
+                }
+                // float: the dot products of a chunk are summed in float, the chunks in double (the norms of later
+                // columns are differences of these sums)
 #pragma unroll
-                    for (int p = 0; p < C; ++p)
+                for (int p = 0; p < C; ++p)
 #pragma unroll
-                        for (int u = 0; u < CPL; ++u) acc[p][u] += y[p] * a[i][u];
+                    for (int u = 0; u < CPL; ++u) acc[p][u] += (double)accf[p][u];
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int rl = w + kWarps * i, t = r0 + rl - jn;
+                if (rl < R && t >= 0 && t < C) {
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) if (valid[u]) topS[t * b + cu[u]] = (double)a[i][u];
                 }
             }
+        }
+    };
+
+    // compact-WY T of the sub-panel [jp, jp + ce) from its block of Gram entries Gq (b x 8) and the T of the columns left of
+    // it:  T22 = (D22 + striu(G22))^-1 by the column recurrence,  T12 = -T11 (G12 T22).  Run by the `nthr` threads with
+    // index t (whole warps) that are synchronised through named barrier 2.
+    auto t_update = [&](int jp, int ce, const T* Gq, int t, int nthr) {
+        if (ce <= 0) return;
+        if (t < 32) {                                      // first warp of the group: lane r = row r of T22 (lane-local recurrence)
+            if (t < ce) {
+                T row[C];
+#pragma unroll
+                for (int q = 0; q < C; ++q) {
+                    T v = (T)0;
+                    if (q < ce && q >= t) {
+                        const T tq = taus[jp + q];
+                        if (q == t) v = tq;
+                        else {
+                            T sacc = (T)0;
+#pragma unroll
+                            for (int cc = 0; cc < C; ++cc) if (cc >= t && cc < q) sacc += row[cc] * Gq[(jp + cc) * 8 + q];
+                            v = -tq * sacc;
+                        }
+                    }
+                    row[q] = v;
+                }
+#pragma unroll
+                for (int q = 0; q < C; ++q) {
+                    T22s[t * 8 + q] = row[q];
+                    if (q < ce) Tt[(jp + q) * b + (jp + t)] = row[q];
+                }
+            } else if (t < C) {
+#pragma unroll
+                for (int q = 0; q < C; ++q) T22s[t * 8 + q] = (T)0;
+            }
+        }
+        asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory");
+        for (int o = t; o < jp * ce; o += nthr) {          // Z = G12 T22
+            const int cc = o / ce, q = o - cc * ce;
+            T z = (T)0;
+            for (int p = 0; p <= q; ++p) z += Gq[cc * 8 + p] * T22s[p * 8 + q];
+            Zs[cc * 8 + q] = z;
+        }
+        asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory");
+        for (int o = t; o < jp * ce; o += nthr) {          // T12 = -T11 Z   (T11 upper triangular; Tt is T transposed)
+            const int q = o / jp, r = o - q * jp;
+            T z0 = (T)0, z1 = (T)0;
+            int cc = r;
+            for (; cc + 1 < jp; cc += 2) { z0 += Tt[cc * b + r] * Zs[cc * 8 + q]; z1 += Tt[(cc + 1) * b + r] * Zs[(cc + 1) * 8 + q]; }
+            if (cc < jp) z0 += Tt[cc * b + r] * Zs[cc * 8 + q];
+            Tt[(jp + q) * b + r] = -(z0 + z1);
         }
     };
 
@@ -204,7 +351,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     (void)tick;
     pass(false, 0, 0, 0);
     BLK_TICK(0);
-    int j = 0;
+    int j = 0, jprev = 0, ceprev = 0;
     unsigned round = 0;
     while (j < kmax) {
         // ---- publish the per-warp dot products ----------------------------------------------------------------
@@ -216,9 +363,9 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         __syncthreads();
         BLK_TICK(1);
         // ---- deterministic all-reduce of [D | Top] -----------------------------------------------------------------
-        auto local_val = [&](int idx) -> T {
+        auto local_val = [&](int idx) -> double {
             if (idx >= CB) return topS[idx - CB];
-            T s = psum[idx];
+            double s = psum[idx];
 #pragma unroll
             for (int q = 1; q < kWarps; ++q) s += psum[q * CB + idx];
             return s;
@@ -231,9 +378,9 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             const int par = (int)(round & 1u);
             // hop 1 (reduce-scatter): slice q of the vector goes to the CTA of rank q in the cluster
             for (int idx = tid; idx < L; idx += nt) {
-                const T v = local_val(idx);
+                const double v = local_val(idx);
                 const int q = idx / SL, e = idx - q * SL;
-                LLSmem<T>::push(map_to_rank(l1_base + in_off(par, crank, e), (unsigned)q), v, seq);
+                LLSmem<double>::push(map_to_rank(l1_base + in_off(par, crank, e), (unsigned)q), v, seq);
             }
             __syncthreads();                              // psum / topS have been read: psum is reused for the partials
             const int mine = max(0, min(SL, L - crank * SL));      // entries of my slice
@@ -244,12 +391,12 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             SpinGuard sg;
             for (int item = tid; item < parts * SL; item += nt) {
                 const int part = item / SL, e = item - part * SL;
-                T s = (T)0;
+                double s = 0.0;
                 if (e < mine) {
                     const int q0 = part * chunk, q1 = min(CS, q0 + chunk);
                     for (int q = q0; q < q1; ++q) {
-                        T v;
-                        while (!LLSmem<T>::try_load(l1_base + in_off(par, q, e), seq, v)) sg.tick();
+                        double v;
+                        while (!LLSmem<double>::try_load(l1_base + in_off(par, q, e), seq, v)) sg.tick();
                         s += v;
                     }
                 }
@@ -257,20 +404,20 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
             }
             __syncthreads();
             for (int e = tid; e < mine; e += nt) {
-                T s = psum[e];
+                double s = psum[e];
                 for (int part = 1; part < parts; ++part) s += psum[part * SL + e];
                 const int idx = crank * SL + e;
                 if (NC > 1) {
                     // level 2: the owners of the same slice in the other clusters exchange their sums through L2
                     char* gs = gbuf + (size_t)par * NC * L * 16;
-                    LLWord<T>::store(gs + ((size_t)cl * L + idx) * 16, s, seq);
-                    T v[kMaxNC];
-                    unsigned pending = (NC >= 32) ? 0xffffffffu : ((1u << NC) - 1u);
+                    LLWord<double>::store(gs + ((size_t)cl * L + idx) * 16, s, seq);
+                    double v[kMaxNC];
+                    unsigned pending = (1u << NC) - 1u;
                     while (pending != 0u) {
 #pragma unroll
                         for (int q = 0; q < kMaxNC; ++q)
                             if ((pending >> q) & 1u) {
-                                if (LLWord<T>::try_load(gs + ((size_t)q * L + idx) * 16, seq, v[q])) pending &= ~(1u << q);
+                                if (LLWord<double>::try_load(gs + ((size_t)q * L + idx) * 16, seq, v[q])) pending &= ~(1u << q);
                             }
                         if (pending != 0u) { sg.tick(); __nanosleep(40); }
                     }
@@ -279,119 +426,126 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                     for (int q = 1; q < kMaxNC; ++q) if (q < NC) s += v[q];
                 }
                 // hop 2 (all-gather): the finished entry goes to every CTA of the cluster
-                for (int q = 0; q < CS; ++q) LLSmem<T>::push(map_to_rank(l1_base + out_off(par, idx), (unsigned)q), s, seq);
+                for (int q = 0; q < CS; ++q) LLSmem<double>::push(map_to_rank(l1_base + out_off(par, idx), (unsigned)q), s, seq);
             }
             for (int idx = tid; idx < L; idx += nt) {
-                T v;
-                while (!LLSmem<T>::try_load(l1_base + out_off(par, idx), seq, v)) sg.tick();
+                double v;
+                while (!LLSmem<double>::try_load(l1_base + out_off(par, idx), seq, v)) sg.tick();
                 red[idx] = v;
             }
             __syncthreads();
         }
         BLK_TICK(2);
-        for (int e = tid; e < CB; e += nt) topS[e] = (T)0;         // next round's top rows: only their owner writes them
-        // ---- the C Householder steps on the exchanged data (warp 0; lane = column) ----------------------------------
+        for (int e = tid; e < CB; e += nt) topS[e] = 0.0;          // next round's top rows: only their owner writes them
+        T* Gcur = Gp + (round & 1u) * (b * 8);
+        // ---- the C Householder steps on the exchanged data (warp 0; lane = column, state in shared memory) ------------
         if (w == 0) {
-            T Tk[CPL][C], Ck[CPL][C];
+            // Downdating form: S[p][k] = (current column j+p, lo part)^T (current column k, lo part) is carried along and
+            // corrected after every reflector (rank-one formulas, no dependent chains); the norm and the dot products of
+            // the next pivot column are then single entries of S.  Top rows and coefficients live in shared memory.
+            double* Ts = red + CB;                         // Top rows, updated in place
+            const double* D = red;
+            double S[C][CPL], d0[C];
 #pragma unroll
-            for (int u = 0; u < CPL; ++u)
+            for (int p = 0; p < C; ++p) {
+                d0[p] = D[p * b + min(j + p, kmax - 1)];   // original ||lo part||^2 of the p-th column of the sub-panel
 #pragma unroll
-                for (int t = 0; t < C; ++t) {
-                    Tk[u][t] = valid[u] ? red[CB + t * b + cu[u]] : (T)0;
-                    Ck[u][t] = (T)0;
+                for (int u = 0; u < CPL; ++u) {
+                    S[p][u] = valid[u] ? D[p * b + cu[u]] : 0.0;
+                    if (valid[u]) Cs[p * b + cu[u]] = 0.0;
                 }
-            const T* D = red;
+            }
+            for (int e = lane; e < b * 8; e += 32) Gcur[e] = (T)0;
+#pragma unroll
+            for (int u = 0; u < CPL; ++u) if (valid[u]) srow[cu[u]] = S[0][u];
+            __syncwarp();
             int done = 0;
             bool active = true;
+            const double guard = guard_ratio(kFloat);
 #pragma unroll
             for (int i = 0; i < C; ++i) {
                 const int ji = j + i;
                 active = active && (ji < kmax);
                 if (active) {                              // warp-uniform
-                    const int lj = ji & 31, uj = ji >> 5;
-                    T mv[C], tj[C];
-#pragma unroll
-                    for (int p = 0; p < C; ++p) {
-                        T sel = Ck[0][p];
-#pragma unroll
-                        for (int u = 1; u < CPL; ++u) sel = (uj == u) ? Ck[u][p] : sel;
-                        const T cv = bcast(sel, lj);
-                        mv[p] = (p <= i) ? (((p == i) ? (T)1 : (T)0) - cv) : (T)0;
-                        T selt = Tk[0][p];
-#pragma unroll
-                        for (int u = 1; u < CPL; ++u) selt = (uj == u) ? Tk[u][p] : selt;
-                        tj[p] = bcast(selt, lj);
-                    }
-                    T gl[CPL];
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) {
-                        T s = (T)0;
-                        if (valid[u]) {
-#pragma unroll
-                            for (int q = 0; q < C; ++q) if (q <= i) s += D[q * b + cu[u]] * mv[q];
-                        }
-                        gl[u] = s;
-                    }
-                    T gv[C];
-#pragma unroll
-                    for (int p = 0; p < C; ++p) {
-                        const int col = min(j + p, kmax - 1);
-                        gv[p] = (p <= i) ? bcast(pick<T, CPL>(gl, col >> 5), col & 31) : (T)0;
-                    }
-                    T s[CPL], dT[CPL];
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) {
-                        T sv = gl[u], dv = (T)0;
-#pragma unroll
-                        for (int p = 0; p < C; ++p) {
-                            if (p <= i) sv -= gv[p] * Ck[u][p];
-                            if (p > i) dv += tj[p] * Tk[u][p];
-                        }
-                        s[u] = sv; dT[u] = dv;
-                    }
-                    const T sji = bcast(pick<T, CPL>(s, uj), lj);
-                    const T dii = D[i * b + ji];
-                    if (i > 0 && !(sji >= guard_ratio<T>() * dii)) {
+                    const double sji = srow[ji];
+                    if (i > 0 && !(sji >= guard * d0[i])) {
                         active = false;                    // too much cancellation: end the sub-panel here
                     } else {
-                        T top2 = (T)0;
+                        double tj[C], mv[C];
 #pragma unroll
-                        for (int t = 0; t < C; ++t) if (t >= i) top2 += tj[t] * tj[t];
-                        const T x0 = tj[i];
-                        const T nrm = sqrt(sji + top2);
-                        const double sgn = -copysign(1.0, (double)x0);
-                        const double u1 = (double)x0 - sgn * (double)nrm;
-                        const T alpha = (T)(1.0 / u1);
-                        const T tau = (T)(-sgn * u1 / (double)nrm);
-                        const T beta = (T)(sgn * (double)nrm);       // R_jj = -sign(x0) ||x||
+                        for (int p = 0; p < C; ++p) {
+                            tj[p] = (p >= i) ? Ts[p * b + ji] : 0.0;
+                            mv[p] = (p <= i) ? (((p == i) ? 1.0 : 0.0) - Cs[p * b + ji]) : 0.0;
+                        }
+                        double t2a = 0.0, t2b = 0.0;
+#pragma unroll
+                        for (int t = i; t < C; t += 2) { t2a += tj[t] * tj[t]; if (t + 1 < C) t2b += tj[t + 1] * tj[t + 1]; }
+                        const double x0 = tj[i];
+                        const double normsq = sji + (t2a + t2b);
+                        const double rn = rsqrt(normsq);
+                        const double nrm = normsq * rn;
+                        const double sgn = -copysign(1.0, x0);
+                        const double u1 = x0 - sgn * nrm;
+                        const double alpha = __drcp_rn(u1);
+                        const double tau = -sgn * u1 * rn;
+                        const double beta = sgn * nrm;                // R_jj = -sign(x0) ||x||
+                        double fav[CPL], xav[CPL];
 #pragma unroll
                         for (int u = 0; u < CPL; ++u) {
+                            fav[u] = 0.0; xav[u] = S[i][u];
+                            if (!valid[u]) continue;
                             const int col = cu[u];
-                            const T dot = Tk[u][i] + alpha * (dT[u] + s[u]);
+                            double dva = 0.0, dvb = 0.0;
+#pragma unroll
+                            for (int t = i + 1; t < C; t += 2) {
+                                dva += tj[t] * Ts[t * b + col];
+                                if (t + 1 < C) dvb += tj[t + 1] * Ts[(t + 1) * b + col];
+                            }
+                            const double dot = Ts[i * b + col] + alpha * ((dva + dvb) + xav[u]);
                             if (col > ji) {
-                                const T f = tau * dot, fa = f * alpha;
-                                Tk[u][i] -= f;
+                                const double f = tau * dot, fa = f * alpha;
+                                fav[u] = fa;
+                                Ts[i * b + col] -= f;
 #pragma unroll
                                 for (int p = 0; p < C; ++p) {
-                                    if (p > i) Tk[u][p] -= fa * tj[p];
-                                    if (p <= i) Ck[u][p] += fa * mv[p];
+                                    if (p > i) Ts[p * b + col] -= fa * tj[p];
+                                    else Cs[p * b + col] += fa * mv[p];
                                 }
                             } else if (col == ji) {
-                                Tk[u][i] = beta;
+                                Ts[i * b + col] = beta;
 #pragma unroll
                                 for (int p = 0; p < C; ++p) {
-                                    if (p > i) Tk[u][p] = alpha * tj[p];
-                                    if (p <= i) Ck[u][p] = ((p == i) ? (T)1 : (T)0) - alpha * mv[p];
+                                    if (p > i) Ts[p * b + col] = alpha * tj[p];
+                                    else Cs[p * b + col] = ((p == i) ? 1.0 : 0.0) - alpha * mv[p];
                                 }
-                                taus[ji] = tau;
-                            } else if (valid[u]) {
-                                Gm[col * b + ji] = dot;    // v_col^T v_ji
+                                taus[ji] = (T)tau;
+                            } else {
+                                Gcur[col * 8 + i] = (T)dot;   // v_col^T v_ji
                             }
+                            fas[col] = fav[u];
+                        }
+                        __syncwarp();
+                        if (i + 1 < C) {
+#pragma unroll
+                            for (int p = i + 1; p < C; ++p) {
+                                const int q = min(j + p, kmax - 1);
+                                const double faq = fas[q], xq = srow[q];
+#pragma unroll
+                                for (int u = 0; u < CPL; ++u) {
+                                    if (cu[u] == ji) S[p][u] = alpha * (xq - faq * sji);
+                                    else S[p][u] = S[p][u] - fav[u] * xq - faq * (xav[u] - fav[u] * sji);
+                                }
+                            }
+                            __syncwarp();                  // everybody has read row i of S and the f's
+#pragma unroll
+                            for (int u = 0; u < CPL; ++u) if (valid[u]) srow[cu[u]] = S[i + 1][u];
+                            __syncwarp();
                         }
                         done = i + 1;
                     }
                 }
             }
+            __syncwarp();
 #pragma unroll
             for (int u = 0; u < CPL; ++u)
                 if (valid[u]) {
@@ -399,24 +553,32 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                     const bool f = col >= j && col < j + done;
 #pragma unroll
                     for (int p = 0; p < C; ++p) {
-                        Kc[p * b + col] = f ? (((p == col - j) ? (T)1 : (T)0) - Ck[u][p]) : -Ck[u][p];
-                        TopF[p * b + col] = Tk[u][p];
+                        const double cv = Cs[p * b + col];
+                        Kc[p * b + col] = (T)(f ? (((p == col - j) ? 1.0 : 0.0) - cv) : -cv);
+                        TopF[p * b + col] = (T)Ts[p * b + col];
                     }
                 }
             if (lane == 0) ctl[0] = done;
+        } else {
+            // meanwhile warps 1-7: the block column of T that belongs to the PREVIOUS sub-panel
+            t_update(jprev, ceprev, Gp + ((round + 1u) & 1u) * (b * 8), tid - 32, nt - 32);
         }
         __syncthreads();
         BLK_TICK(3);
         const int ceff = ctl[0];
         pass(true, j, ceff, j + ceff);
+        jprev = j; ceprev = ceff;
         j += ceff;
         round += 1;
         BLK_TICK(4);
         if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[8] += 1;
     }
+    __syncthreads();
+    if (w != 0) t_update(jprev, ceprev, Gp + ((round + 1u) & 1u) * (b * 8), tid - 32, nt - 32);   // T of the last sub-panel
 
-    // ---- epilogue (as panel_reg_kernel) --------------------------------------------------------------------------
+    // ---- epilogue --------------------------------------------------------------------------------------------------
     if (G > 1) cg::this_cluster().sync();                 // nobody pushes words into the staging area any more
+    else __syncthreads();
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int rl = w + kWarps * i;
@@ -439,30 +601,40 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 const int row = r0 + rl;
                 A[(size_t)c * lda + row] = (c >= row) ? Ps[rl * ld + c] : (T)0;
             }
+    // V2 = V S^T with S = -T:  V2[r][c] = -sum_{k = c .. min(r, b-1)} V[r][k] T[c][k].  One thread per row: the row of V
+    // sits in Ps (odd leading dimension: conflict-free), every T entry is a broadcast load shared by the 32 rows of a warp;
+    // no dependent chain (the per-column kernels solve a triangular system per row here).
     __syncthreads();
-    // every row x of V2 solves x (D + U)^T = -v by back substitution (T^-1 = diag(1/tau) + striu(V^T V)); two threads
-    // per row split the inner sums (even / odd k) to shorten the dependent chains.  The loops are warp-uniform (shuffles).
-    for (int base = 0; base < 2 * R; base += nt) {
-        const int item = base + tid;
-        const bool act = item < 2 * R;
-        const int rl = act ? (item >> 1) : 0, half = item & 1;
-        const int row = r0 + rl;
+    for (int rl = tid; rl < R; rl += nt) {
+        const int row = r0 + rl, khi = min(b - 1, row);
         T* x = Ps + rl * ld;
-        const int khi = min(kmax - 1, row);
-        for (int c = kmax - 1; c >= 0; --c) {
-            T s0 = (T)0, s1 = (T)0;
-            if (act && c <= khi) {
-                int k = c + 1 + half;
-                for (; k + 2 <= khi; k += 4) { s0 += x[k] * Gm[c * b + k]; s1 += x[k + 2] * Gm[c * b + k + 2]; }
-                for (; k <= khi; k += 2) s0 += x[k] * Gm[c * b + k];
+        if (row < b) {                                    // explicit unit diagonal, zeros above it
+            x[row] = (T)1;
+            for (int k = row + 1; k < b; ++k) x[k] = (T)0;
+        }
+        for (int c0 = 0; c0 <= khi; c0 += 8) {
+            T o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = (T)0;
+            for (int k = c0; k <= khi; ++k) {
+                const T xv = x[k];
+                const T* tk = Tt + k * b + c0;             // T[c0 + q][k], zero for c0 + q > k  (16-byte aligned: b, c0 multiples of 8)
+                T tv[8];
+                if constexpr (kFloat) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(tk), v1 = *reinterpret_cast<const float4*>(tk + 4);
+                    tv[0] = v0.x; tv[1] = v0.y; tv[2] = v0.z; tv[3] = v0.w; tv[4] = v1.x; tv[5] = v1.y; tv[6] = v1.z; tv[7] = v1.w;
+                } else {
+#pragma unroll
+                    for (int p2 = 0; p2 < 4; ++p2) {
+                        const double2 v = *reinterpret_cast<const double2*>(tk + 2 * p2);
+                        tv[2 * p2] = v.x; tv[2 * p2 + 1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] += xv * tv[q];
             }
-            T s = s0 + s1;
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (act && half == 0) {
-                const T vc = (row == c) ? (T)1 : x[c];
-                x[c] = (c <= khi) ? (-vc - s) * taus[c] : (T)0;
-            }
-            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[c0 + q] = -o[q];   // columns c0 .. c0+7 are not read again (k >= c0 + 8 from here on)
         }
     }
     __syncthreads();
@@ -475,15 +647,6 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     }
     BLK_TICK(5);
     if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[9] += 1;
-}
-
-inline size_t blk_smem_bytes(int rows, int b, size_t esz, const BlkShape& sh, size_t* stage_out) {
-    size_t stage = (size_t)rows * (b + 1) * esz;
-    if (sh.CS * sh.NC > 1 && sh.exch_bytes > stage) stage = sh.exch_bytes;
-    stage = (stage + 15) & ~(size_t)15;
-    *stage_out = stage;
-    const size_t CB = (size_t)kC * b;
-    return stage + ((size_t)b * b + b + kWarps * CB + CB + 2 * CB + CB + CB) * esz + 64;
 }
 
 template <typename T, bool kTrans, int RPT, int CPL>
@@ -500,8 +663,7 @@ int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
         if (NC > 1 && c->overlap_safe) return 1;
     }
     const BlkShape sh = blk_shape(b, CS, NC);
-    size_t stage = 0;
-    const size_t smem = blk_smem_bytes(ROWS, b, sizeof(T), sh, &stage);
+    const size_t smem = blk_smem(ROWS, b, sizeof(T), sh).total;
     if (smem > 227 * 1024) return 1;
     auto kern = panel_blk_kernel<T, kTrans, RPT, CPL>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -533,7 +695,7 @@ int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
         if (NC > max_clusters) return 1;
     }
     char* gbuf = reinterpret_cast<char*>(c->red2);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch, stage);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch);
     if (e != cudaSuccess) { cudaGetLastError(); return 1; }
     c->launches++;
     return 0;
@@ -563,7 +725,10 @@ int launch_panel_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaSt
     }
     if (fits(8)) return launch_blk<T, kTrans, 8, 2>(c, a, lda, m, b, V, V2, stream);
     if (sizeof(T) == 8 || fits(16)) return launch_blk<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream);
-    if (fits(32)) return launch_blk<float, kTrans, 32, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
+    // float, band 64: 256 rows per CTA (several clusters beyond 4096 rows) as long as the CTAs fit the GPU; 512 rows per CTA
+    // (128 registers of panel per thread: spills) only for the 65536-row panels of the multi-GPU configuration
+    if (fits(32) || (!c->overlap_safe && (m + 255) / 256 <= c->num_sms - 4))
+        return launch_blk<float, kTrans, 32, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
     return launch_blk<float, kTrans, 64, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
 }
 template int launch_panel_blk<float, false>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t);

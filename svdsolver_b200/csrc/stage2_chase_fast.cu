@@ -23,6 +23,17 @@ namespace svdb200 {
 namespace {
 using namespace s2;
 
+#ifndef SVDB_S2_TIMING
+#define SVDB_S2_TIMING 0
+#endif
+// per-phase cycle counters of interior RIGHT ops of CTA 1 (debug builds: -DSVDB_S2_TIMING=1); every slot has one writer
+__device__ long long g_s2f_dbg[16];
+#define S2F_T() (SVDB_S2_TIMING ? clock64() : 0ll)
+#define S2F_ADD(k, v)                                                   \
+    do {                                                                \
+        if (SVDB_S2_TIMING && blockIdx.x == 1) g_s2f_dbg[k] += (v);     \
+    } while (0)
+
 constexpr int kC = 32;                 // band
 constexpr int kMain = 256;             // main threads: warps 0-3 = F half, warps 4-7 = N half
 constexpr int kFastThreads = kMain + 32;
@@ -31,28 +42,44 @@ __device__ __forceinline__ void bar_n_helper() { asm volatile("bar.sync 1, 160;"
 
 // Helper warp: reflector of the next op from its Householder vector xv (lane l holds x_l), exactly as
 // reflector_scalars + build_h do it (sequential unfused sum of squares in index order; scalars in double; H = I - tau w w^T
-// with w_0 = 1, w_i = x_i * alpha).
+// with w_0 = 1, w_i = x_i * alpha).  The shared-memory pipe is busy with the operands of the window product, so every
+// value another lane holds is fetched in ONE batch of vector loads (x goes through a 32-element staging row) instead of one
+// shuffle per step: the dependent chains then run on registers only.
 template <typename T>
-__device__ __forceinline__ void helper_reflector(T xv, T* __restrict__ Hn, int ldh, bool guard) {
+__device__ __forceinline__ void helper_reflector(T xv, T* __restrict__ xst, T* __restrict__ Hn, int ldh, bool guard) {
     const int lane = threadIdx.x & 31;
+    xst[lane] = xv;
+    __syncwarp();
+    T x[kC];
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int r = 0; r < kC; r += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xst + r);
+            x[r] = v.x; x[r + 1] = v.y; x[r + 2] = v.z; x[r + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kC; r += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(xst + r);
+            x[r] = v.x; x[r + 1] = v.y;
+        }
+    }
     T acc = (T)0;
 #pragma unroll
-    for (int r = 0; r < kC; ++r) {
-        const T v = __shfl_sync(0xffffffffu, xv, r);
-        acc = RN<T>::add(acc, RN<T>::mul(v, v));
-    }
+    for (int r = 0; r < kC; ++r) acc = RN<T>::add(acc, RN<T>::mul(x[r], x[r]));
     T alpha, tau;
     if (guard && acc == (T)0) { alpha = (T)0; tau = (T)0; }
-    else householder_scalars<T>(__shfl_sync(0xffffffffu, xv, 0), RN<T>::sqrt(acc), alpha, tau);
+    else householder_scalars<T>(x[0], RN<T>::sqrt(acc), alpha, tau);
     const T mtau = -tau;
     const T wl = (lane == 0) ? (T)1 : RN<T>::mul(xv, alpha);
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
-        const T wi = __shfl_sync(0xffffffffu, wl, i);
+        const T wi = (i == 0) ? (T)1 : RN<T>::mul(x[i], alpha);
         T h = RN<T>::mul(RN<T>::add((T)0, RN<T>::mul(wi, wl)), mtau);
         if (i == lane) h = RN<T>::add((T)1, h);
         Hn[i * ldh + lane] = h;
     }
+    __syncwarp();
 }
 
 template <typename T>
@@ -65,6 +92,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stage2_fast_kernel(T* __restr
     T* Hb0 = WL + c * ldl;                      // two H buffers [c][c+1]: the current op's and the next op's
     T* Hb1 = Hb0 + c * ldh;
     T* sc = Hb1 + c * ldh;                      // alpha, tau (generic path)
+    T* xst = sc + 8;                            // helper: staging row for the next Householder vector (16-byte aligned)
     const int tid = threadIdx.x;
     const bool is_main = tid < kMain, is_helper = !is_main;
     const bool f_warp = tid < kMain / 2, n_warp = is_main && !f_warp;
@@ -89,11 +117,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) stage2_fast_kernel(T* __restr
             // ================= RIGHT(p): rows [r0,r2) x cols [r1,r2), window = [F; N] ===================
             {
                 const int q = 2 * p;
+                const long long t_op0 = S2F_T();
                 if (i > 0 && tid == 0) seen = wait_progress(&prog[i - 1], q + 4, seen);
+                const long long t_polled = S2F_T();
                 __syncthreads();
+                const long long t_start = S2F_T();
                 const int nc = r2 - r1, nr = r2 - r0, have = fr;
                 const bool interior = (have == c) && (nr == 2 * c) && (nc == c);
                 if (interior) {
+                    if (tid == 0) { S2F_ADD(0, t_polled - t_op0); S2F_ADD(9, t_start - t_polled); S2F_ADD(7, 1); if (!hready) S2F_ADD(10, 1); }
                     T nv[8];
                     if (n_warp) {                 // new block: rows [c,2c) of the window, 8 elements per thread
 #pragma unroll
@@ -105,24 +137,40 @@ __global__ void __launch_bounds__(kFastThreads, 1) stage2_fast_kernel(T* __restr
                         if (is_main) build_h<T>(WR, 1, c, sc, Hc, ldh, tx, ty, tys);
                         __syncthreads();
                     }
+                    const long long t_h = S2F_T();
+                    long long t_done = 0;
                     if (f_warp) {                 // F half: finished rows [r0,r1) -> global
                         window_product<T, kC>(WR, ldr, Hc, ldh, c, c, c, 16, 8,
                                               [&](int r, int cc, T v) { st_cg(&A[(size_t)(r0 + r) * N + (r1 + cc)], v); }, tid);
+                        t_done = S2F_T();
+                        if (tid == 0) { S2F_ADD(11, t_h - t_start); S2F_ADD(1, t_done - t_h); }
                     } else if (n_warp) {
 #pragma unroll
                         for (int u = 0; u < 8; ++u) WR[(c + (ht >> 5) + 4 * u) * ldr + (ht & 31)] = nv[u];
+                        const long long t_ld = S2F_T();
                         bar_n_helper();
+                        const long long t_b = S2F_T();
                         window_product<T, kC>(WR + c * ldr, ldr, Hc, ldh, c, c, c, 16, 8,
                                               [&](int r, int cc, T v) { WL[r * ldl + cc] = v; }, ht);
+                        t_done = S2F_T();
+                        if (tid == kMain / 2) { S2F_ADD(3, t_ld - t_start); S2F_ADD(12, t_b - t_ld); S2F_ADD(4, t_done - t_b); }
                     } else {                      // helper: x' = column 0 of N * H  (LEFT(p)'s Householder vector)
                         bar_n_helper();
+                        const long long t_b = S2F_T();
                         const int lane = tid & 31;
+                        T xo[kC], yo[kC];
+#pragma unroll
+                        for (int k = 0; k < c; ++k) { xo[k] = WR[(c + lane) * ldr + k]; yo[k] = Hc[k * ldh]; }
                         T acc = (T)0;
-#pragma unroll 8
-                        for (int k = 0; k < c; ++k) acc = RN<T>::add(acc, RN<T>::mul(WR[(c + lane) * ldr + k], Hc[k * ldh]));
-                        helper_reflector<T>(acc, Hn, ldh, complete != 0);
+#pragma unroll
+                        for (int k = 0; k < c; ++k) acc = RN<T>::add(acc, RN<T>::mul(xo[k], yo[k]));
+                        const long long t_x = S2F_T();
+                        helper_reflector<T>(acc, xst, Hn, ldh, complete != 0);
+                        t_done = S2F_T();
+                        if (tid == kMain) { S2F_ADD(6, t_b - t_start); S2F_ADD(13, t_x - t_b); S2F_ADD(5, t_done - t_x); }
                     }
                     __syncthreads();
+                    if (tid == 0) { S2F_ADD(2, S2F_T() - t_done); S2F_ADD(8, S2F_T() - t_op0); }
                     { T* t = Hc; Hc = Hn; Hn = t; }
                     hready = true;
                 } else {
@@ -199,10 +247,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) stage2_fast_kernel(T* __restr
                     } else {                      // helper: x'' = row 0 of H * N  (RIGHT(p+1)'s Householder vector)
                         bar_n_helper();
                         const int lane = tid & 31;
+                        T xo[kC], yo[kC];
+#pragma unroll
+                        for (int k = 0; k < c; ++k) { xo[k] = Hc[k]; yo[k] = WL[k * ldl + c + lane]; }
                         T acc = (T)0;
-#pragma unroll 8
-                        for (int k = 0; k < c; ++k) acc = RN<T>::add(acc, RN<T>::mul(Hc[k], WL[k * ldl + c + lane]));
-                        helper_reflector<T>(acc, Hn, ldh, complete != 0);
+#pragma unroll
+                        for (int k = 0; k < c; ++k) acc = RN<T>::add(acc, RN<T>::mul(xo[k], yo[k]));
+                        helper_reflector<T>(acc, xst, Hn, ldh, complete != 0);
                     }
                     fr = c;
                     __syncthreads();
@@ -248,11 +299,18 @@ __global__ void __launch_bounds__(kFastThreads, 1) stage2_fast_kernel(T* __restr
 
 }  // namespace
 
+int stage2_fast_debug_read(long long* out16) {
+    long long z[16] = {};
+    if (cudaMemcpyFromSymbol(out16, g_s2f_dbg, sizeof(z)) != cudaSuccess) return 1;
+    cudaMemcpyToSymbol(g_s2f_dbg, z, sizeof(z));
+    return 0;
+}
+
 // returns 0 when it ran, 1 when the shape is outside this kernel's range (the caller runs stage2_chase_kernel)
 template <typename T>
 int stage2_chase_fast(Ctx* c, T* a, size_t n, size_t band, int* prog) {
     if (band != (size_t)kC || n < 2 * band + 2) return 1;
-    const size_t smem = (size_t)(2 * kC * (kC + 1) + kC * (2 * kC + 1) + 2 * kC * (kC + 1) + 8) * sizeof(T);
+    const size_t smem = (size_t)(2 * kC * (kC + 1) + kC * (2 * kC + 1) + 2 * kC * (kC + 1) + 8 + kC + 8) * sizeof(T);
     auto kern = stage2_fast_kernel<T>;
     SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

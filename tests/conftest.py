@@ -131,3 +131,48 @@ def band_rel(a, ref, band):
     for k in range(band + 1):
         num = max(num, float(np.abs(np.diagonal(a, k).astype(np.float64) - np.diagonal(ref, k).astype(np.float64)).max()))
     return num / float(np.abs(ref).max())
+
+
+def band_sign_scaling(a, ref, band):
+    """Diagonal +-1 scalings (d1, d2) with d1[i] * a[i, j] * d2[j] ~ ref[i, j] on the band: a maximum spanning tree of the
+    bipartite row / column graph of the band (weights |ref[i, j]|, Prim) fixes one sign per row and column through the
+    LARGEST entries.  Householder's sign rule (svd_serial.h:194: s = -sign(x0)) is discontinuous at x0 = 0, so a pivot
+    that is tiny relative to the rounding noise of a float path can come out with either sign; everything downstream is
+    equivariant under B -> D1 B D2 (SURVEY 8a'), which is also what the reference's own `mse` check ignores."""
+    import heapq
+    n = a.shape[0]
+    a64, r64 = a.astype(np.float64), ref.astype(np.float64)
+    d1, d2 = np.zeros(n), np.zeros(n)
+    d1[0] = 1.0
+    heap = []
+
+    def push_row(i):
+        for j in range(i, min(n, i + band + 1)):
+            if d2[j] == 0:
+                heapq.heappush(heap, (-abs(r64[i, j]), 0, i, j))
+
+    def push_col(j):
+        for i in range(max(0, j - band), j + 1):
+            if d1[i] == 0:
+                heapq.heappush(heap, (-abs(r64[i, j]), 1, i, j))
+
+    push_row(0)
+    while heap:
+        _, kind, i, j = heapq.heappop(heap)
+        sgn = 1.0 if a64[i, j] * r64[i, j] >= 0 else -1.0
+        if kind == 0 and d2[j] == 0:          # row i known -> column j
+            d2[j] = d1[i] * sgn
+            push_col(j)
+        elif kind == 1 and d1[i] == 0:        # column j known -> row i
+            d1[i] = d2[j] * sgn
+            push_row(i)
+    d1[d1 == 0] = 1.0
+    d2[d2 == 0] = 1.0
+    return d1, d2
+
+
+def band_rel_mod_signs(a, ref, band):
+    """band_rel after the best +-1 row / column scaling; also returns how many rows / columns were flipped."""
+    d1, d2 = band_sign_scaling(a, ref, band)
+    scaled = (a.astype(np.float64) * d1[:, None]) * d2[None, :]
+    return band_rel(scaled, ref, band), int((d1 < 0).sum() + (d2 < 0).sum())

@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-from conftest import band_rel
+from conftest import band_rel, band_rel_mod_signs
 from svdsolver_b200.synth import uniform_matrix
 
 pytestmark = pytest.mark.gpu
@@ -92,14 +92,27 @@ def test_many_pipeline_stage2_bit_exact_at_bench_sizes(capi, oracle, suf):
 
 
 # ------------------------------------------------------------------ panel order vs oracle at a larger size ----
-@pytest.mark.parametrize("n,b,suf", [(640, 32, "f64"), (640, 32, "f32"), (768, 64, "f64"), (512, 8, "f32")])
-def test_stage1_panel_order_vs_oracle_larger(capi, oracle, n, b, suf):
+@pytest.mark.parametrize("blocked", [1, 0])
+@pytest.mark.parametrize("n,b,suf", [(640, 32, "f64"), (640, 32, "f32"), (768, 64, "f64"), (768, 64, "f32"), (512, 8, "f32"), (512, 8, "f64"),
+                                     (1024, 32, "f64"), (512, 16, "f32")])
+def test_stage1_panel_order_vs_oracle_larger(capi, oracle, n, b, suf, blocked):
+    """Signed parity with the oracle's panel order for both panel kernels (blocked: one exchange per 8 columns; per-column).
+    Double: every sign must agree.  Float: a pivot that is tiny relative to fp32 round-off may legitimately come out with the
+    other sign (the rule s = -sign(x0) is discontinuous; 1e-5 relative noise against ~10^3 pivots of size O(1)), which
+    flips one row / column of the band; such flips are accepted only as an exact D1 B D2 scaling, at the same tolerance."""
+    import ctypes
     a = uniform_matrix(n, n, 586 + n + b, 0.0, 5.0, DT[suf])
     ref = oracle.brd_p1_panel(a, b)
     with capi.Handle(n, b, DT[suf]) as h:
+        assert capi.lib().svdb200_set_panel_kernel(h.h, ctypes.c_int(blocked)) == 0
         out = h.dense_to_band(a, b, capi.ORDER_PANEL)
-    assert band_rel(out, ref, b) <= TOL[suf]
     assert np.abs(np.tril(out, -1)).max() == 0
+    rel = band_rel(out, ref, b)
+    if suf == "f64":
+        assert rel <= TOL[suf]
+    elif rel > TOL[suf]:
+        rel2, flips = band_rel_mod_signs(out, ref, b)
+        assert rel2 <= TOL[suf] and flips <= 8, (rel, rel2, flips)
 
 
 @pytest.mark.parametrize("n", [24, 33])

@@ -101,3 +101,70 @@ if __name__ == "__main__":
     for jj in range(16):
         Q = Q @ (np.eye(300) - tb[jj] * np.outer(Vb[:, jj], Vb[:, jj]))
     print("orth", np.abs(Q.T @ Q - np.eye(300)).max(), "recon", np.abs(Q @ np.vstack([np.triu(Ab[:16]), np.zeros((284, 16))]) - A0).max())
+
+
+def blk2(A, C=8, guard=1.0 / 64, dtype=np.float64):
+    """Same blocked factorisation with the DOWNDATING form of the small algebra (what the kernel runs): instead of
+    re-deriving every dot product from the exchanged D through the coefficient matrix, the C x b matrix
+    S[p][k] = (current column j+p, lo part)^T (current column k, lo part) is carried along and updated after each reflector
+    (rank-one formulas, no dependent chains); norms and dots of the next pivot are then single entries of S."""
+    A = A.astype(dtype).copy(); m, b = A.shape
+    Gm = np.zeros((b, b), dtype); taus = np.zeros(b, dtype)
+    j = 0; rounds = 0
+    while j < b:
+        lo = j + C
+        D = A[lo:, j:j + C].T @ A[lo:, :] if lo < m else np.zeros((C, b), dtype)
+        if D.shape[0] < C:
+            D = np.vstack([D, np.zeros((C - D.shape[0], b), dtype)])
+        Top = np.zeros((C, b), dtype); nt = min(C, m - j); Top[:nt] = A[j:j + nt, :]
+        Cm = np.zeros((C, b), dtype)
+        S = D.copy()
+        d0 = np.array([D[p, min(j + p, b - 1)] for p in range(C)])
+        done = 0
+        for i in range(C):
+            ji = j + i
+            if ji >= b: break
+            sji = S[i, ji]
+            if i > 0 and not (sji >= guard * d0[i]):
+                break
+            tj = Top[:, ji].copy()
+            nrm = np.sqrt(sji + (tj[i:] ** 2).sum()); x0 = tj[i]
+            sgn = -np.copysign(1.0, x0); u1 = float(x0) - sgn * float(nrm)
+            alpha = dtype(1.0 / u1); tau = dtype(-sgn * u1 / float(nrm)); beta = dtype(sgn * float(nrm))
+            mv = -Cm[:, ji].copy(); mv[i] += 1; mv[i + 1:] = 0
+            xa = S[i, :].copy()                              # x_lo^T (column k, lo)
+            dT = tj[i + 1:] @ Top[i + 1:, :]
+            dot = Top[i, :] + alpha * (dT + xa)
+            fa = np.zeros(b, dtype)
+            for col in range(b):
+                if col > ji:
+                    f = tau * dot[col]; fa[col] = f * alpha
+                    Top[i, col] -= f; Top[i + 1:, col] -= fa[col] * tj[i + 1:]; Cm[:i + 1, col] += fa[col] * mv[:i + 1]
+                elif col == ji:
+                    Top[i, col] = beta; Top[i + 1:, col] = alpha * tj[i + 1:]
+                    e = np.zeros(C, dtype); e[i] = 1
+                    Cm[:, col] = e - alpha * mv; Cm[i + 1:, col] = 0
+                    taus[ji] = tau
+                else:
+                    Gm[col, ji] = dot[col]
+            # downdate S for the rows of the later pivots
+            for p in range(i + 1, C):
+                q = j + p
+                if q >= b: break
+                for col in range(b):
+                    if col == ji:
+                        S[p, col] = alpha * (xa[q] - fa[q] * sji)
+                    else:
+                        S[p, col] = S[p, col] - fa[col] * xa[q] - fa[q] * (xa[col] - fa[col] * sji)
+            done = i + 1
+        K = -Cm.copy(); keep = np.ones(b, dtype)
+        for col in range(j, j + done):
+            K[:, col] = -Cm[:, col]; K[col - j, col] += 1; keep[col] = 0
+        if lo < m:
+            X = A[lo:, j:j + C].copy()
+            if X.shape[1] < C:
+                X = np.hstack([X, np.zeros((X.shape[0], C - X.shape[1]), dtype)])
+            A[lo:, :] = A[lo:, :] * keep + X @ K
+        A[j:j + nt, :] = Top[:nt]
+        j += done; rounds += 1
+    return A, Gm, taus, rounds

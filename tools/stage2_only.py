@@ -40,3 +40,15 @@ if any(out):
              "barrier + build H + store N + barrier", "window product", "barrier after product"]
     for i, nme in enumerate(names):
         print(f"  phase {i} {nme:44s} {out[i]:12d} cycles {100.0*out[i]/tot:5.1f}%")
+
+out = (ctypes.c_longlong * 16)()
+capi.lib().svdb200_debug_stage2_fast_timing(out)
+if any(out):
+    cnt = max(out[7], 1)
+    names = {0: "thread 0: poll predecessor", 9: "barrier after poll", 11: "inline scalars + H (first interior op only)", 1: "F warps: product of the forwarded block",
+             2: "thread 0: wait at the closing barrier", 8: "whole op (thread 0)", 3: "N warps: fetch new block (issue .. stored)",
+             12: "N warps: wait for helper at bar 1", 4: "N warps: product of the new block", 6: "helper: op start .. bar 1",
+             13: "helper: 32 dot products (next Householder vector)", 5: "helper: sum of squares + scalars + H"}
+    print(f"  fast kernel, interior RIGHT ops of CTA 1: {cnt} ops ({out[10]} without a prepared H)")
+    for k, nme in names.items():
+        print(f"    {nme:52s} {out[k] / cnt:9.0f} cycles per op")
