@@ -103,6 +103,16 @@ int svdb200_bidiagonalize_f64(svdb200_handle h, double* a, size_t m, size_t n, s
 int svdb200_bidiagonalize_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, size_t band, int order, float* d_dev, float* e_dev);
 int svdb200_bidiagonalize_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, size_t band, int order, double* d_dev, double* e_dev);
 
+/* ---- One-stage bidiagonalisation (cross-check path) -------------------------------------------------
+ * Replaces csc586::serial::brd<T> (svd_serial.h:233-266; its blocked / OpenMP twins block_brd 442, gpu::brd svd_cpu.h:441
+ * compute the same factorisation): Golub-Kahan Householder bidiagonalisation, one column reflector and one row reflector
+ * per step, same sign convention.  Runs the stage-1 panel driver with band 1 (O(n) small launches: a cross-check for the
+ * two-stage path, not a throughput path).  `a` is overwritten by the bidiagonalised matrix; d (n), e (n-1) optional. */
+int svdb200_bidiagonalize_onestage_f32(svdb200_handle h, float* a, size_t m, size_t n, float* d, float* e);
+int svdb200_bidiagonalize_onestage_f64(svdb200_handle h, double* a, size_t m, size_t n, double* d, double* e);
+int svdb200_bidiagonalize_onestage_dev_f32(svdb200_handle h, float* a_dev, size_t m, size_t n, float* d_dev, float* e_dev);
+int svdb200_bidiagonalize_onestage_dev_f64(svdb200_handle h, double* a_dev, size_t m, size_t n, double* d_dev, double* e_dev);
+
 /* The same for a LIST of independent matrices (sizes may differ; every n[i] <= max_n and band | n[i]): stage 2 of matrix i
  * runs on its own stream beside stage 1 of matrix i+1 (both are latency-bound at moderate n), and in the host-pointer
  * variant the H2D / D2H copies are double-buffered behind the kernels.  a, d, e are host arrays of `count` pointers
@@ -190,7 +200,9 @@ int svdb200_debug_stage2_fast_timing(long long* out16);
 /* Singular values of the bidiagonal (svdb200_bidiag_qr_*, svdb200_svdvals_*): method 0 = automatic (the
  * reference's zero-shift QR sweeps, serial::qrd svd_serial.h:368, for n <= auto_limit, bisection on the
  * Golub-Kahan form above: zero-shift QR needs ~n log(1/tol) sweeps), 1 = always zero-shift QR, 2 = always
- * bisection.  auto_limit == 0 keeps the current limit (default 1024). */
+ * bisection, 3 = implicit SHIFTED QR (Golub-Kahan steps with shifts from the trailing block, pipelined sweeps, double
+ * arithmetic for both element types; the reference is zero-shift only, svd_serial.h:314-333).  auto_limit == 0 keeps the
+ * current limit (default 1024). */
 int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit);
 /* Unit test of the tcgen05 building blocks (TMA box -> swizzled shared memory -> UMMA descriptors -> TMEM ->
  * tcgen05.ld): D(128 x 64) = A(128 x 32) B(32 x 64) in one TF32 pass.  a_mn/b_mn select the operand storage:
@@ -224,6 +236,18 @@ int svdb200_dist_destroy(svdb200_dist_handle h);
 size_t svdb200_dist_local_cols(size_t n, size_t band, int rank, int nranks);
 int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle h, float* a_local_dev, size_t n, size_t band);
 int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle h, double* a_local_dev, size_t n, size_t band);
+/* Hand-off to stage 2 ("band gathered to one GPU first"): after svdb200_dist_dense_to_band_dev_*, the b+1
+ * diagonals are collected from all ranks (one ncclAllGather of n (b+1) elements) into packed band storage on EVERY rank:
+ * packed[gc * (band+1) + t] = A[gc - band + t][gc], t = 0..band (device, n x (band+1)). */
+int svdb200_dist_gather_band_dev_f32(svdb200_dist_handle h, const float* a_local_dev, float* packed_dev);
+int svdb200_dist_gather_band_dev_f64(svdb200_dist_handle h, const double* a_local_dev, double* packed_dev);
+/* Singular values of a block-cyclically distributed matrix: stage 1 on all ranks, band gathered, stage 2 + singular
+ * values on rank 0 (those stages are one sequential wavefront over an O(n b) band: one GPU per matrix).  sigma_dev (n,
+ * device) is written on rank 0 only; a_local is overwritten by the rank's part of the band matrix. */
+int svdb200_dist_svdvals_dev_f32(svdb200_dist_handle h, float* a_local_dev, float* sigma_dev);
+int svdb200_dist_svdvals_dev_f64(svdb200_dist_handle h, double* a_local_dev, double* sigma_dev);
+/* run-time switches of the handle's single-GPU stages (see svdb200_set_stage2_schedule / _qr_method / _tc05); -1 keeps */
+int svdb200_dist_configure(svdb200_dist_handle h, int stage2_schedule, int qr_method, int tc05_mode);
 int svdb200_dist_set_stream(svdb200_dist_handle h, void* cuda_stream);
 long long svdb200_dist_launch_count(svdb200_dist_handle h);
 

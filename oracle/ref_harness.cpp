@@ -14,6 +14,7 @@
 //   csc586::parallel::brd_p2<T>   svd_parallel.h:640     (band -> bidiagonal bulge chasing)
 //   csc586::serial::qrd<float>    svd_serial.h:368       (zero-shift QR diagonalisation)
 //   csc586::serial::householder   svd_serial.h:189
+//   csc586::serial::brd<T>        svd_serial.h:233       (one-stage Golub-Kahan bidiagonalisation)
 //   csc586::gpu::brd_p1           svd_cpu.h:370          (full-height panel dense -> band, float)
 //   csc586::gpu::brd_p2<T>        svd_cpu.h:631
 #include <cstring>
@@ -51,6 +52,17 @@ int p2(T* a, size_t n, size_t b, T* d, T* e) {
     if (e) std::memcpy(e, B.e.data(), B.e.size() * sizeof(T));
     return 0;
 }
+// csc586::serial::brd<T> (svd_serial.h:233-266): the one-stage Golub-Kahan Householder bidiagonalisation
+template <typename T>
+int serial_brd(T* a, size_t n, T* d, T* e) {
+    csc586::Matrix<T> A(a, n, n);
+    A.parallel = false;
+    auto B = csc586::serial::brd<T>(A);
+    flatten_into(A, a);
+    if (d) std::memcpy(d, B.d.data(), B.d.size() * sizeof(T));
+    if (e) std::memcpy(e, B.e.data(), B.e.size() * sizeof(T));
+    return 0;
+}
 template <typename T>
 int hh(const T* x, size_t len, T* w, T* H, T* tau) {
     csc586::Matrix<T> X(x, len, 1);
@@ -69,6 +81,8 @@ int svdref_brd_p1_f32(float* a, size_t n, size_t t) { return p1<float>(a, n, t);
 int svdref_brd_p1_f64(double* a, size_t n, size_t t) { return p1<double>(a, n, t); }
 int svdref_brd_p2_f32(float* a, size_t n, size_t b, float* d, float* e) { return p2<float>(a, n, b, d, e); }
 int svdref_brd_p2_f64(double* a, size_t n, size_t b, double* d, double* e) { return p2<double>(a, n, b, d, e); }
+int svdref_serial_brd_f32(float* a, size_t n, float* d, float* e) { return serial_brd<float>(a, n, d, e); }
+int svdref_serial_brd_f64(double* a, size_t n, double* d, double* e) { return serial_brd<double>(a, n, d, e); }
 int svdref_householder_f32(const float* x, size_t len, float* w, float* H, float* tau) { return hh<float>(x, len, w, H, tau); }
 int svdref_householder_f64(const double* x, size_t len, double* w, double* H, double* tau) { return hh<double>(x, len, w, H, tau); }
 

@@ -17,6 +17,8 @@ extern "C" {
     size_t svdo_brd_p2_schedule_##S(size_t n, size_t band, long long* out, size_t cap);              \
     /* NOT the reference: same windows and arithmetic, every bulge chased to the end (checker for the complete schedule) */ \
     int svdo_brd_p2_complete_##S(T* A, size_t n, size_t band, T* d, T* e);                           \
+    /* csc586::serial::brd<T>  svd_serial.h:233-266 (one-stage Golub-Kahan bidiagonalisation) */     \
+    int svdo_brd_serial_##S(T* A, size_t n, T* d, T* e);                                             \
     /* csc586::serial::householder<T>  svd_serial.h:189-216 */                                       \
     int svdo_householder_##S(const T* x, size_t len, T* w, T* H, T* tau);                            \
     /* parallel::qr / lq  svd_parallel.h:133-226; qr_apply / lq_apply 243-281 */                      \

@@ -195,6 +195,37 @@ int FN(svdo_panel_lq)(T* A, size_t m, size_t n, T* S, T* U) {
     free(work);
     return 0;
 }
+/* csc586::serial::brd<T>, svd_serial.h:233-266: one-stage Golub-Kahan bidiagonalisation.  For every column j: explicit H
+ * of A[j:m, j] applied from the left to A[j:m, j:n] (H.mm(minor)); then, for j < n-1, explicit H of the row A[j, j+1:n]
+ * applied from the right to A[j:m, j+1:n] (minor.mm(H)).  Length-1 reflectors flip a sign (tau = 2). */
+int FN(svdo_brd_serial)(T* A, size_t n, T* d, T* e) {
+    T* w = (T*)malloc(sizeof(T) * n);
+    T* H = (T*)malloc(sizeof(T) * n * n);
+    T* minor = (T*)malloc(sizeof(T) * n * n);
+    T* prod = (T*)malloc(sizeof(T) * n * n);
+    if (!w || !H || !minor || !prod) { free(w); free(H); free(minor); free(prod); return 1; }
+    for (size_t j = 0; j < n; ++j) {
+        T tau;
+        size_t len = n - j, cols = n - j;
+        FN(householder)(A + j * n + j, n, len, w, &tau);
+        FN(hh_transform)(w, len, tau, H);
+        for (size_t r = 0; r < len; ++r) memcpy(minor + r * cols, A + (j + r) * n + j, sizeof(T) * cols);
+        FN(mm)(prod, cols, H, len, minor, cols, len, len, cols);
+        for (size_t r = 0; r < len; ++r) memcpy(A + (j + r) * n + j, prod + r * cols, sizeof(T) * cols);
+        if (j + 1 < n) {
+            size_t rl = n - j - 1;                       /* reflector length = columns j+1 .. n-1 */
+            FN(householder)(A + j * n + j + 1, 1, rl, w, &tau);
+            FN(hh_transform)(w, rl, tau, H);
+            for (size_t r = 0; r < len; ++r) memcpy(minor + r * rl, A + (j + r) * n + j + 1, sizeof(T) * rl);
+            FN(mm)(prod, rl, minor, rl, H, rl, len, rl, rl);
+            for (size_t r = 0; r < len; ++r) memcpy(A + (j + r) * n + j + 1, prod + r * rl, sizeof(T) * rl);
+        }
+    }
+    for (size_t i = 0; i < n; ++i) { if (d) d[i] = A[i * n + i]; if (e && i + 1 < n) e[i] = A[i * n + i + 1]; }
+    free(w); free(H); free(minor); free(prod);
+    return 0;
+}
+
 int FN(svdo_householder)(const T* x, size_t len, T* w, T* H, T* tau) {
     FN(householder)(x, 1, len, w, tau);
     if (H) FN(hh_transform)(w, len, *tau, H);

@@ -134,6 +134,15 @@ class Handle:
         self._check(self._fn("bidiagonalize")(self.h, _p(a), Z(a.shape[0]), Z(n), Z(band), ctypes.c_int(order), _p(d), _p(e)))
         return a, d, e
 
+    def bidiagonalize_onestage(self, a):
+        """one-stage Golub-Kahan bidiagonalisation (serial::brd order): returns (A_out, d, e)"""
+        a = self._mat(a)
+        n = a.shape[1]
+        d = np.zeros(n, self.dtype)
+        e = np.zeros(max(n - 1, 0), self.dtype)
+        self._check(self._fn("bidiagonalize_onestage")(self.h, _p(a), Z(a.shape[0]), Z(n), _p(d), _p(e)))
+        return a, d, e
+
     def bidiagonalize_inplace(self, a_ptr, n, band, d_ptr, e_ptr, order=ORDER_PANEL):
         """Host-pointer call on caller-owned (e.g. pinned) buffers given as raw addresses."""
         self._check(self._fn("bidiagonalize")(self.h, _p(a_ptr), Z(n), Z(n), Z(band), ctypes.c_int(order), _p(d_ptr), _p(e_ptr)))
@@ -248,7 +257,7 @@ class Handle:
         self._check(lib().svdb200_set_stage2_schedule(self.h, ctypes.c_int(mode)))
 
     def set_qr_method(self, method, auto_limit=0):
-        """0 auto, 1 zero-shift QR sweeps (reference algorithm), 2 bisection."""
+        """0 auto, 1 zero-shift QR sweeps (reference algorithm), 2 bisection, 3 implicit shifted QR."""
         self._check(lib().svdb200_set_qr_method(self.h, ctypes.c_int(method), Z(auto_limit)))
 
     def launch_count(self):

@@ -833,6 +833,34 @@ int svdb200_synchronize(svdb200_handle h) {
         SVDB_TRY(stage1_dispatch<T>(c, a, n, band, order));                                                              \
         return stage2_chase<T>(c, a, n, band, d, e);                                                                     \
     }                                                                                                                    \
+    int svdb200_bidiagonalize_onestage_dev_##S(svdb200_handle h, T* a, size_t m, size_t n, T* d, T* e) {                 \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, 1, dtype_of<T>()));                                                               \
+        c->onestage = 1;                                                                                                 \
+        const int st = stage1_panel_order<T>(c, a, n, 1);                                                                \
+        c->onestage = 0;                                                                                                 \
+        if (st != 0) return st;                                                                                          \
+        return extract_bidiagonal<T>(c, a, n, d, e);                                                                     \
+    }                                                                                                                    \
+    int svdb200_bidiagonalize_onestage_##S(svdb200_handle h, T* a, size_t m, size_t n, T* d, T* e) {                     \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a) return SVDB200_E_ARG;                                                                                    \
+        SVDB_TRY(check_square(c, m, n, 1, dtype_of<T>()));                                                               \
+        SVDB_TRY(ensure_staging(c));                                                                                     \
+        T* ad = reinterpret_cast<T*>(c->a_dev);                                                                          \
+        SVDB_CHECK(c, cudaMemcpyAsync(ad, a, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream));                     \
+        c->onestage = 1;                                                                                                 \
+        int st = stage1_panel_order<T>(c, ad, n, 1);                                                                     \
+        c->onestage = 0;                                                                                                 \
+        if (st == 0) st = extract_bidiagonal<T>(c, ad, n, reinterpret_cast<T*>(c->d), reinterpret_cast<T*>(c->e));       \
+        if (st != 0) return st;                                                                                          \
+        SVDB_CHECK(c, cudaMemcpyAsync(a, ad, sizeof(T) * n * n, cudaMemcpyDeviceToHost, c->stream));                     \
+        if (d) SVDB_CHECK(c, cudaMemcpyAsync(d, c->d, sizeof(T) * n, cudaMemcpyDeviceToHost, c->stream));                \
+        if (e && n > 1) SVDB_CHECK(c, cudaMemcpyAsync(e, c->e, sizeof(T) * (n - 1), cudaMemcpyDeviceToHost, c->stream)); \
+        SVDB_CHECK(c, cudaStreamSynchronize(c->stream));                                                                 \
+        return 0;                                                                                                        \
+    }                                                                                                                    \
     int svdb200_bidiagonalize_many_dev_##S(svdb200_handle h, size_t count, T* const* a, const size_t* n, size_t band,    \
                                            int order, T* const* d, T* const* e) {                                        \
         SVDB_ENTER(T)                                                                                                    \
@@ -1006,7 +1034,7 @@ int svdb200_set_stage2_schedule(svdb200_handle h, int mode) {
 }
 
 int svdb200_set_qr_method(svdb200_handle h, int method, size_t auto_limit) {
-    if (!h || method < 0 || method > 2) return SVDB200_E_ARG;
+    if (!h || method < 0 || method > 3) return SVDB200_E_ARG;
     Ctx* c = reinterpret_cast<Ctx*>(h);
     c->qr_method = method;
     if (auto_limit > 0) c->qr_auto_limit = auto_limit;

@@ -74,6 +74,7 @@ struct Ctx {
     cudaStream_t s2_stream[kLanes] = {};
     int* s2_prog[kLanes] = {};              // progress counters per lane
     cudaEvent_t s2ev[4 + kLanes] = {};
+    int onestage = 0;                       // stage-1 driver in the one-stage Golub-Kahan order (band 1, no skipped row reflector)
     int s2_ready = 0;                       // the pipeline's streams / counters / sub-handles below exist (all or nothing)
     int panel_blk = 1;                      // blocked panel kernel (one exchange per 8 columns, stage1_panel_blk.cu) where the shape allows
     int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
@@ -199,9 +200,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsi
 
 // ---- internal entry points (one per .cu) ----------------------------------------------------------
 template <typename T> int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e);
+template <typename T> int extract_bidiagonal(Ctx* c, const T* a, size_t n, T* d, T* e);
 template <typename T> int stage2_chase_fast(Ctx* c, T* a, size_t n, size_t band, int* prog);   // 0 ran, 1 shape not covered
 template <typename T> int bidiag_qr(Ctx* c, T* d, T* e, size_t n, T* sigma);
 template <typename T> int bidiag_bisect(Ctx* c, const T* d, const T* e, size_t n, T* sigma);
+template <typename T> int bidiag_sqr(Ctx* c, T* d, T* e, size_t n, T* sigma);
 template <typename T> int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band);
 template <typename T> int stage1_tile_order(Ctx* c, T* a, size_t n, size_t band);
 template <typename T> int gemm_tn(Ctx* c, const T* v, const T* cm, size_t ldc, size_t mrows, size_t ncols, size_t b, T* w);

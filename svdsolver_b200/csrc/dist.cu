@@ -67,6 +67,10 @@ struct Dist {
     void* sendbuf = nullptr;     // band x ncl_max
     void* ut_loc = nullptr;      // ncl_max x band
     void* u2_loc = nullptr;      // band x ncl_max
+    void* vv = nullptr;          // [V | V S^T] of a QR panel, contiguous (2 x n x band): ONE broadcast per panel
+    void* bandsend = nullptr;    // ncl_max x (band+1) : this rank's band columns, packed
+    void* bandall = nullptr;     // nranks x ncl_max x (band+1) : all-gather landing zone
+    void* dense = nullptr;       // rank 0, svdvals only: n x n staging for stage 2 (allocated on first use)
     size_t ncl_max = 0;
 };
 
@@ -132,6 +136,42 @@ __global__ void scatter_local_kernel(const T* __restrict__ panel, const T* __res
     ut_loc[lc * b + r] = ut[gc * b + r];
 }
 
+// ---- band hand-off to stage 2 ("band gathered to one GPU first") --------------------------------------
+// Packed band storage, column by column: packed[gc * (b+1) + t] = A[gc - b + t][gc], t = 0 .. b (zero above the matrix) --
+// the b+1 diagonals stage 1 leaves, n (b+1) elements instead of n^2.
+template <typename T>
+__global__ void pack_band_local_kernel(const T* __restrict__ a, size_t ldl, size_t ncl, int b, int rank, int P, T* __restrict__ out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncl * (size_t)(b + 1)) return;
+    const size_t lc = e / (b + 1);
+    const int t = (int)(e - lc * (b + 1));
+    const size_t gc = ((lc / b) * P + rank) * b + lc % b;
+    const long long row = (long long)gc - b + t;
+    out[e] = row >= 0 ? a[(size_t)row * ldl + lc] : (T)0;
+}
+// gathered [rank][lc][t] -> packed [gc][t] (global column order)
+template <typename T>
+__global__ void unpack_band_global_kernel(const T* __restrict__ gathered, size_t n, size_t ncl_max, int b, int P, T* __restrict__ packed) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (size_t)(b + 1)) return;
+    const size_t gc = e / (b + 1);
+    const int t = (int)(e - gc * (b + 1));
+    const size_t gb = gc / b;
+    const int r = (int)(gb % P);
+    const size_t lc = (gb / P) * b + gc % b;
+    packed[e] = gathered[((size_t)r * ncl_max + lc) * (b + 1) + t];
+}
+// packed band -> dense n x n (zero elsewhere)
+template <typename T>
+__global__ void band_to_dense_kernel(const T* __restrict__ packed, size_t n, int b, T* __restrict__ dense) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (size_t)(b + 1)) return;
+    const size_t gc = e / (b + 1);
+    const int t = (int)(e - gc * (b + 1));
+    const long long row = (long long)gc - b + t;
+    if (row >= 0) dense[(size_t)row * n + gc] = packed[e];
+}
+
 // Look-ahead (same scheme as the single-GPU driver, stage1_panel.cu): the part of an update that the NEXT panel lives in
 // is applied first; the panel (and its collective) then runs on the high-priority aux stream s1 while the main stream s0
 // finishes the much larger rest of the update.
@@ -147,8 +187,8 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
     const int P = d->nranks, rk = d->rank, b = (int)band;
     const size_t nb = n / band;
     const size_t ldl = svdb200_dist_local_cols(n, band, rk, P);
-    T* V = reinterpret_cast<T*>(c->v);
-    T* V2 = reinterpret_cast<T*>(c->v2);
+    T* V = reinterpret_cast<T*>(d->vv);                  // QR reflectors: [V (m x b) | V S^T (m x b)] back to back, one message
+    T* V2 = V;                                           // set per panel: V + m * band
     T* Vl = reinterpret_cast<T*>(c->vb);
     T* V2l = reinterpret_cast<T*>(c->v2b);
     T* W = reinterpret_cast<T*>(c->w);
@@ -168,12 +208,9 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
     auto qr_panel_and_bcast = [&](size_t k) -> int {
         const size_t o = k * band, m = n - o;
         const int owner = (int)(k % P);
-        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, V, V2, s1)));
-        if (P > 1) {
-            // V and V2 are adjacent allocations only by accident: broadcast them separately
-            SVDB_NCCL(d, nccl().Broadcast(V, V, m * band, nccl_type<T>(), owner, d->comm, s1));
-            SVDB_NCCL(d, nccl().Broadcast(V2, V2, m * band, nccl_type<T>(), owner, d->comm, s1));
-        }
+        T* v2k = V + m * band;
+        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, V, v2k, s1)));
+        if (P > 1) SVDB_NCCL(d, nccl().Broadcast(V, V, 2 * m * band, nccl_type<T>(), owner, d->comm, s1));
         if (ahead) SVDB_CHECK(c, cudaEventRecord(evQ, s1));
         return 0;
     };
@@ -183,6 +220,7 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
         const bool has_lq = (o + band < n - 1);
         const size_t lb0 = first_local_block_after(k, rk, P);        // first local block with global index > k
         const size_t ncl = ldl - lb0 * band;                         // local trailing columns
+        V2 = V + m * band;
         // ---- QR half-step ------------------------------------------------------------------------------
         if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, evQ, 0));   // reflectors of panel k have arrived
         T* A2 = a + o * ldl + lb0 * band;
@@ -256,6 +294,60 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
     return 0;
 }
 
+// every rank ends up with the packed band (n x (b+1), global column order) in `packed`
+template <typename T>
+int dist_gather_band(Dist* d, const T* a, T* packed) {
+    Ctx* c = d->ctx;
+    const int P = d->nranks, rk = d->rank, b = (int)d->band;
+    const size_t n = d->n, ldl = svdb200_dist_local_cols(n, d->band, rk, P);
+    T* sendb = reinterpret_cast<T*>(d->bandsend);
+    T* all = reinterpret_cast<T*>(d->bandall);
+    const size_t cnt = d->ncl_max * (size_t)(b + 1);
+    cudaStream_t s0 = c->stream;
+    SVDB_CHECK(c, cudaMemsetAsync(sendb, 0, cnt * sizeof(T), s0));
+    if (ldl > 0) {
+        const size_t tot = ldl * (size_t)(b + 1);
+        pack_band_local_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s0>>>(a, ldl, ldl, b, rk, P, sendb);
+        c->launches++;
+    }
+    if (P > 1) SVDB_NCCL(d, nccl().AllGather(sendb, all, cnt, nccl_type<T>(), d->comm, s0));
+    else SVDB_CHECK(c, cudaMemcpyAsync(all, sendb, cnt * sizeof(T), cudaMemcpyDeviceToDevice, s0));
+    const size_t tot = n * (size_t)(b + 1);
+    unpack_band_global_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s0>>>(all, n, d->ncl_max, b, P, packed);
+    c->launches++;
+    SVDB_CHECK(c, cudaGetLastError());
+    return 0;
+}
+
+// stage 1 distributed, then the band goes to rank 0, which runs stage 2 and the singular values (replicas only there:
+// one sequential wavefront over an O(n b) band)
+template <typename T>
+int dist_svdvals(Dist* d, T* a, T* sigma) {
+    Ctx* c = d->ctx;
+    const size_t n = d->n, band = d->band;
+    SVDB_TRY(dist_stage1<T>(d, a, n, band));
+    if (!d->dense && d->rank == 0) SVDB_CHECK(c, cudaMalloc(&d->dense, sizeof(T) * n * n));
+    void* pk = nullptr;
+    SVDB_CHECK(c, cudaMalloc(&pk, sizeof(T) * n * (band + 1)));
+    T* packed = reinterpret_cast<T*>(pk);
+    int st = dist_gather_band<T>(d, a, packed);
+    if (st == 0 && d->rank == 0) {
+        T* dense = reinterpret_cast<T*>(d->dense);
+        cudaError_t e = cudaMemsetAsync(dense, 0, sizeof(T) * n * n, c->stream);
+        if (e != cudaSuccess) st = cuda_status(c, e, "cudaMemsetAsync(dense)");
+        if (st == 0) {
+            const size_t tot = n * (band + 1);
+            band_to_dense_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(packed, n, (int)band, dense);
+            c->launches++;
+            st = stage2_chase<T>(c, dense, n, band, reinterpret_cast<T*>(c->d), reinterpret_cast<T*>(c->e));
+        }
+        if (st == 0) st = bidiag_qr<T>(c, reinterpret_cast<T*>(c->d), reinterpret_cast<T*>(c->e), n, sigma);
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(pk);
+    return st;
+}
+
 }  // namespace
 }  // namespace svdb200
 
@@ -300,6 +392,9 @@ int svdb200_dist_create(svdb200_dist_handle* out, int device, int rank, int nran
     if (e == cudaSuccess) e = cudaMalloc(&d->sendbuf, es * band * d->ncl_max);
     if (e == cudaSuccess) e = cudaMalloc(&d->ut_loc, es * band * d->ncl_max);
     if (e == cudaSuccess) e = cudaMalloc(&d->u2_loc, es * band * d->ncl_max);
+    if (e == cudaSuccess) e = cudaMalloc(&d->vv, es * 2 * (n + 256) * band);
+    if (e == cudaSuccess) e = cudaMalloc(&d->bandsend, es * d->ncl_max * (band + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d->bandall, es * (size_t)nranks * d->ncl_max * (band + 1));
     if (e != cudaSuccess) { int s2 = cuda_status(d->ctx, e, "cudaMalloc(dist)"); svdb200_dist_destroy(reinterpret_cast<svdb200_dist_handle>(d)); return s2; }
     if (nranks > 1) {
         ncclUniqueId id;
@@ -316,7 +411,7 @@ int svdb200_dist_destroy(svdb200_dist_handle h) {
     Dist* d = reinterpret_cast<Dist*>(h);
     if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
     if (d->comm) nccl().CommDestroy(d->comm);
-    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc};
+    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc, d->vv, d->bandsend, d->bandall, d->dense};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (d->ctx) svdb200_destroy(reinterpret_cast<svdb200_handle>(d->ctx));
     delete d;
@@ -343,6 +438,35 @@ int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle h, double* a, size_t 
     if (d->ctx->dtype != SVDB200_F64 || n != d->n || band != d->band) return SVDB200_E_ARG;
     SVDB_CHECK(d->ctx, cudaSetDevice(d->ctx->device));
     return dist_stage1<double>(d, a, n, band);
+}
+
+#define SVDB_DIST_TYPED(T, S, CODE)                                                                                  \
+    int svdb200_dist_gather_band_dev_##S(svdb200_dist_handle h, const T* a_local, T* packed) {                       \
+        if (!h || !a_local || !packed) return SVDB200_E_ARG;                                                         \
+        Dist* d = reinterpret_cast<Dist*>(h);                                                                        \
+        if (d->ctx->dtype != CODE) return SVDB200_E_ARG;                                                             \
+        SVDB_CHECK(d->ctx, cudaSetDevice(d->ctx->device));                                                           \
+        return dist_gather_band<T>(d, a_local, packed);                                                              \
+    }                                                                                                                \
+    int svdb200_dist_svdvals_dev_##S(svdb200_dist_handle h, T* a_local, T* sigma) {                                  \
+        if (!h || !a_local) return SVDB200_E_ARG;                                                                    \
+        Dist* d = reinterpret_cast<Dist*>(h);                                                                        \
+        if (d->ctx->dtype != CODE || (d->rank == 0 && !sigma)) return SVDB200_E_ARG;                                 \
+        SVDB_CHECK(d->ctx, cudaSetDevice(d->ctx->device));                                                           \
+        return dist_svdvals<T>(d, a_local, sigma);                                                                   \
+    }
+SVDB_DIST_TYPED(float, f32, SVDB200_F32)
+SVDB_DIST_TYPED(double, f64, SVDB200_F64)
+#undef SVDB_DIST_TYPED
+
+int svdb200_dist_configure(svdb200_dist_handle h, int stage2_schedule, int qr_method, int tc05_mode) {
+    if (!h) return SVDB200_E_ARG;
+    Dist* d = reinterpret_cast<Dist*>(h);
+    svdb200_handle ch = reinterpret_cast<svdb200_handle>(d->ctx);
+    if (stage2_schedule >= 0) SVDB_TRY(svdb200_set_stage2_schedule(ch, stage2_schedule));
+    if (qr_method >= 0) SVDB_TRY(svdb200_set_qr_method(ch, qr_method, 0));
+    if (tc05_mode >= 0) SVDB_TRY(svdb200_set_tc05(ch, tc05_mode, 0));
+    return 0;
 }
 
 }  // extern "C"

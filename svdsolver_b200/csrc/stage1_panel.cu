@@ -403,7 +403,9 @@ int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
     for (size_t k = 0; k < n; k += band) {
         const size_t m = n - k;                 // panel height
         const size_t nc = n - k - band;         // columns right of the QR panel
-        const bool has_lq = (k + band < n - 1);
+        // svd_cpu.h:396 skips the LQ half-step when only one column is left; the one-stage Golub-Kahan order
+        // (serial::brd, svd_serial.h:248) still applies that length-1 reflector (a sign flip): c->onestage
+        const bool has_lq = c->onestage ? (k + band < n) : (k + band < n - 1);
         if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, c->lev[1], 0));   // QR panel k is done
         if (nc > 0) {
             T* A2 = a + k * n + k + band;

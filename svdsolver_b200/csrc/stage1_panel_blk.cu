@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, char* __restrict__ gbuf, int NC,
                  unsigned epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int ROWS = RPT * kWarps, C = kC, CH = (RPT < 8 ? RPT : 8);
     constexpr bool kFloat = sizeof(T) == 4;
+    constexpr int ROWS = RPT * kWarps, C = kC, CH = kFloat ? (RPT < 8 ? RPT : 8) : (RPT < 4 ? RPT : 4);   // rows per staging chunk
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31, w = tid >> 5;
     const int G = gridDim.x, g = blockIdx.x;
     const int CS = G / NC, cl = g / CS, crank = g - cl * CS;
@@ -605,36 +605,61 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     // sits in Ps (odd leading dimension: conflict-free), every T entry is a broadcast load shared by the 32 rows of a warp;
     // no dependent chain (the per-column kernels solve a triangular system per row here).
     __syncthreads();
-    for (int rl = tid; rl < R; rl += nt) {
-        const int row = r0 + rl, khi = min(b - 1, row);
-        T* x = Ps + rl * ld;
-        if (row < b) {                                    // explicit unit diagonal, zeros above it
+    for (int rl = tid; rl < R; rl += nt) {                // explicit unit diagonal, zeros above it (rows of the top block only)
+        const int row = r0 + rl;
+        if (row < b) {
+            T* x = Ps + rl * ld;
             x[row] = (T)1;
             for (int k = row + 1; k < b; ++k) x[k] = (T)0;
         }
-        for (int c0 = 0; c0 <= khi; c0 += 8) {
-            T o[8];
+    }
+    __syncthreads();
+    {
+        // tpr threads per row share its b/8 column chunks (short slices leave most threads idle otherwise); all outputs of
+        // a thread stay in registers until every thread of the row has read the row
+        const int tpr = (4 * R <= nt) ? 4 : ((2 * R <= nt) ? 2 : 1);
+        const int nch = b / 8;
+        for (int base = 0; base < R * tpr; base += nt) {
+            const int item = base + tid;
+            const bool act = item < R * tpr;
+            const int rl = act ? item / tpr : 0, sub = item % tpr;
+            const int row = r0 + rl, khi = min(b - 1, row);
+            T* x = Ps + rl * ld;
+            T o[8][8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = (T)0;
-            for (int k = c0; k <= khi; ++k) {
-                const T xv = x[k];
-                const T* tk = Tt + k * b + c0;             // T[c0 + q][k], zero for c0 + q > k  (16-byte aligned: b, c0 multiples of 8)
-                T tv[8];
-                if constexpr (kFloat) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(tk), v1 = *reinterpret_cast<const float4*>(tk + 4);
-                    tv[0] = v0.x; tv[1] = v0.y; tv[2] = v0.z; tv[3] = v0.w; tv[4] = v1.x; tv[5] = v1.y; tv[6] = v1.z; tv[7] = v1.w;
-                } else {
+            for (int qc = 0; qc < 8; ++qc) {
+                const int c0 = (sub + qc * tpr) * 8;
 #pragma unroll
-                    for (int p2 = 0; p2 < 4; ++p2) {
-                        const double2 v = *reinterpret_cast<const double2*>(tk + 2 * p2);
-                        tv[2 * p2] = v.x; tv[2 * p2 + 1] = v.y;
+                for (int q = 0; q < 8; ++q) o[qc][q] = (T)0;
+                if (act && sub + qc * tpr < nch && c0 <= khi) {
+                    for (int k = c0; k <= khi; ++k) {
+                        const T xv = x[k];
+                        const T* tk = Tt + k * b + c0;         // T[c0 + q][k], zero for c0 + q > k  (16-byte aligned)
+                        T tv[8];
+                        if constexpr (kFloat) {
+                            const float4 v0 = *reinterpret_cast<const float4*>(tk), v1 = *reinterpret_cast<const float4*>(tk + 4);
+                            tv[0] = v0.x; tv[1] = v0.y; tv[2] = v0.z; tv[3] = v0.w; tv[4] = v1.x; tv[5] = v1.y; tv[6] = v1.z; tv[7] = v1.w;
+                        } else {
+#pragma unroll
+                            for (int p2 = 0; p2 < 4; ++p2) {
+                                const double2 v = *reinterpret_cast<const double2*>(tk + 2 * p2);
+                                tv[2 * p2] = v.x; tv[2 * p2 + 1] = v.y;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[qc][q] += xv * tv[q];
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] += xv * tv[q];
             }
+            __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) x[c0 + q] = -o[q];   // columns c0 .. c0+7 are not read again (k >= c0 + 8 from here on)
+            for (int qc = 0; qc < 8; ++qc) {
+                const int c0 = (sub + qc * tpr) * 8;
+                if (act && sub + qc * tpr < nch) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[c0 + q] = -o[qc][q];
+                }
+            }
         }
     }
     __syncthreads();

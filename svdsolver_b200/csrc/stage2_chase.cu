@@ -260,6 +260,18 @@ int stage2_chase_batched(Ctx* c, T* a, size_t n, size_t band, T* d, T* e, int co
 template <typename T>
 int stage2_chase(Ctx* c, T* a, size_t n, size_t band, T* d, T* e) { return stage2_chase_batched<T>(c, a, n, band, d, e, 1); }
 
+// d = diag(A), e = diag(A, 1) of a device matrix (what Bidiagonal{A.diag(), A.diag(1)} returns, svd_serial.h:264)
+template <typename T>
+int extract_bidiagonal(Ctx* c, const T* a, size_t n, T* d, T* e) {
+    if (!d && !e) return 0;
+    extract_bidiagonal_kernel<T><<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream>>>(a, (int)n, d, e);
+    SVDB_CHECK(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+template int extract_bidiagonal<float>(Ctx*, const float*, size_t, float*, float*);
+template int extract_bidiagonal<double>(Ctx*, const double*, size_t, double*, double*);
+
 template int stage2_chase_batched<float>(Ctx*, float*, size_t, size_t, float*, float*, int);
 template int stage2_chase_batched<double>(Ctx*, double*, size_t, size_t, double*, double*, int);
 template int stage2_chase<float>(Ctx*, float*, size_t, size_t, float*, float*);

@@ -38,6 +38,16 @@ def gather_block_cyclic(parts, band, n):
     return out
 
 
+def unpack_band(packed, n, band):
+    """packed band storage (n x (band+1): packed[gc, t] = A[gc - band + t, gc]) -> dense n x n numpy array"""
+    out = np.zeros((n, n), packed.dtype)
+    for t in range(band + 1):
+        k = band - t                      # super-diagonal index
+        rows = np.arange(0, n - k)
+        out[rows, rows + k] = packed[k:, t]
+    return out
+
+
 def exchange_unique_id(rank, nranks):
     """Rank 0 creates the ncclUniqueId (through the C ABI) and broadcasts it with torch.distributed."""
     import torch.distributed as dist
@@ -76,6 +86,22 @@ class DistHandle:
                                                                                 ctypes.c_size_t(self.band))
         if st != 0:
             raise capi.SvdB200Error(st, capi.lib().svdb200_strerror(st).decode())
+
+    def gather_band_dev(self, a_local_ptr, packed_ptr):
+        st = getattr(capi.lib(), f"svdb200_dist_gather_band_dev_{self.suf}")(self.h, ctypes.c_void_p(a_local_ptr), ctypes.c_void_p(packed_ptr))
+        if st != 0:
+            raise capi.SvdB200Error(st, capi.lib().svdb200_strerror(st).decode())
+
+    def svdvals_dev(self, a_local_ptr, sigma_ptr):
+        """stage 1 on all ranks, band gathered, stage 2 + singular values on rank 0 (sigma_ptr: device, n; rank 0 only)"""
+        st = getattr(capi.lib(), f"svdb200_dist_svdvals_dev_{self.suf}")(self.h, ctypes.c_void_p(a_local_ptr), ctypes.c_void_p(sigma_ptr or 0))
+        if st != 0:
+            raise capi.SvdB200Error(st, capi.lib().svdb200_strerror(st).decode())
+
+    def configure(self, stage2_schedule=-1, qr_method=-1, tc05_mode=-1):
+        st = capi.lib().svdb200_dist_configure(self.h, ctypes.c_int(stage2_schedule), ctypes.c_int(qr_method), ctypes.c_int(tc05_mode))
+        if st != 0:
+            raise capi.SvdB200Error(st, "svdb200_dist_configure")
 
     def launch_count(self):
         return int(capi.lib().svdb200_dist_launch_count(self.h))

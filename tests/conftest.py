@@ -66,6 +66,16 @@ class Oracle:
         assert rc == 0
         return x, d, e
 
+    def brd_serial(self, a):
+        """csc586::serial::brd (one-stage Golub-Kahan): returns (A_out, d, e)"""
+        x = np.ascontiguousarray(a).copy()
+        n = x.shape[0]
+        d = np.zeros(n, x.dtype)
+        e = np.zeros(n - 1, x.dtype)
+        rc = getattr(self.lib, "svdo_brd_serial_" + self.suf(x))(self.ptr(x), ctypes.c_size_t(n), self.ptr(d), self.ptr(e))
+        assert rc == 0
+        return x, d, e
+
     def qrd(self, d, e):
         d = np.ascontiguousarray(d).copy()
         e = np.ascontiguousarray(e).copy()

@@ -62,3 +62,18 @@ def test_gloo_world2_layout_and_rendezvous():
     for p in procs:
         p.join(timeout=60)
     assert all(ok1 and ok2 for _, ok1, ok2 in res), res
+
+
+def test_unpack_band_layout():
+    """packed band storage of the stage-2 hand-off: packed[gc, t] = A[gc - band + t, gc]"""
+    from svdsolver_b200 import distributed as D
+    rng = np.random.default_rng(1)
+    for n, b in ((50, 4), (64, 32), (33, 1)):
+        a = np.triu(np.tril(rng.normal(size=(n, n)), b))
+        packed = np.zeros((n, b + 1))
+        for gc in range(n):
+            for t in range(b + 1):
+                r = gc - b + t
+                if r >= 0:
+                    packed[gc, t] = a[r, gc]
+        assert np.array_equal(D.unpack_band(packed, n, b), a)

@@ -491,3 +491,74 @@ def test_bidiagonalize_many_matches_single_calls(capi, oracle, suf, schedule):
         band = oracle.brd_p1_panel(mats[i], b)
         _, dr, er = oracle.brd_p2(band, b)
         assert np.abs(dd[i].cpu().numpy() - dr).max() <= 1e-10 * np.abs(dr).max()
+
+
+# ------------------------------------------------------------------ implicit shifted QR ------------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n", [2, 3, 17, 100, 640, 2000])
+def test_bidiag_shifted_qr_vs_lapack(capi, suf, n):
+    """svdb200_set_qr_method(3): Golub-Kahan steps with shifts, pipelined sweeps; sigma vs LAPACK on the same bidiagonal"""
+    rng = np.random.default_rng(n)
+    d = (rng.random(n) * 5).astype(DT[suf])
+    e = (rng.random(n - 1) * 5 - 2.5).astype(DT[suf])
+    if n >= 17:
+        d[n // 3] = 0          # an exact zero on the diagonal (rotated out) and a split window
+        e[n // 2] = 0
+    ref = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+    with handle(capi, n, 1, suf) as h:
+        h.set_qr_method(3)
+        sigma, sweeps = h.bidiag_qr(d, e)
+    assert np.all(np.diff(sigma) <= 0)
+    assert 0 < sweeps <= 12 * n + 64          # a few sweeps per value (zero-shift QR: ~n log(1/tol) sweeps per value)
+    tol = 3e-7 if suf == "f32" else 1e-13
+    assert np.abs(sigma.astype(np.float64) - ref).max() <= tol * ref[0]
+
+
+@pytest.mark.parametrize("n", [64, 320, 640])
+def test_bidiag_shifted_qr_float_vs_reference_qrd(capi, n):
+    """against the reference's own (zero-shift) serial::qrd<float> golden values, at the reference tolerance"""
+    g = np.load(os.path.join(GOLDEN, "golden_qrd.npz"))
+    de = uniform_matrix(2, n, 586 + n, 0.0, 5.0, np.float32)
+    with handle(capi, n, 1, "f32") as h:
+        h.set_qr_method(3)
+        sigma, _ = h.bidiag_qr(de[0], de[1, : n - 1])
+    ref = g[f"qrd_sigma_{n}"]
+    assert np.abs(sigma - ref).max() <= 1e-4 * ref[0]
+
+
+def test_svdvals_chain_with_shifted_qr(capi):
+    """full chain (complete stage-2 schedule) with the shifted QR as the sigma solver == LAPACK on the input"""
+    n, b = 768, 32
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, np.float64)
+    s0 = np.linalg.svd(a, compute_uv=False)
+    with handle(capi, n, b, "f64") as h:
+        h.set_stage2_schedule(1)
+        h.set_qr_method(3)
+        sig, _ = h.svdvals(a.copy(), b)
+    assert np.abs(sig - s0).max() <= 1e-11 * s0[0]
+
+
+# ------------------------------------------------------------------ one-stage path (SURVEY 8f rank 4) -----------------
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n", [8, 48, 96, 200])
+def test_onestage_bidiagonalization_vs_oracle(capi, oracle, suf, n):
+    """svdb200_bidiagonalize_onestage_* vs the oracle's serial::brd restatement (pinned to the compiled reference): signed
+    parity of d and e, zeros outside the bidiagonal up to round-off; and the two-stage path agrees with it in sigma."""
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    ref, dr, er = oracle.brd_serial(a)
+    with handle(capi, n, 8, suf) as h:
+        out, d, e = h.bidiagonalize_onestage(a)
+        if n % 8 == 0:
+            h.set_stage2_schedule(1)
+            sig2, _ = h.svdvals(a.copy(), 8)
+        else:
+            sig2 = None
+    scale = float(np.abs(dr).max())
+    tol = TOL[suf]
+    assert np.abs(d.astype(np.float64) - dr).max() <= tol * scale and np.abs(e.astype(np.float64) - er).max() <= tol * scale
+    assert np.abs(np.tril(out, -1)).max() <= tol * scale and np.abs(np.triu(out, 2)).max() <= tol * scale
+    s1 = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+    s0 = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+    assert np.abs(s1 - s0).max() <= (2e-5 if suf == "f32" else 1e-12) * s0[0]
+    if sig2 is not None:
+        assert np.abs(sig2.astype(np.float64) - s1).max() <= (2e-5 if suf == "f32" else 1e-11) * s0[0]

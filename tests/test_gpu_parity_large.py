@@ -99,7 +99,7 @@ def test_stage1_panel_order_vs_oracle_larger(capi, oracle, n, b, suf, blocked):
     """Signed parity with the oracle's panel order for both panel kernels (blocked: one exchange per 8 columns; per-column).
     Double: every sign must agree.  Float: a pivot that is tiny relative to fp32 round-off may legitimately come out with the
     other sign (the rule s = -sign(x0) is discontinuous; 1e-5 relative noise against ~10^3 pivots of size O(1)), which
-    flips one row / column of the band; such flips are accepted only as an exact D1 B D2 scaling, at the same tolerance."""
+    re-signs rows / columns of the band; such flips are accepted only as an exact D1 B D2 scaling, at the same tolerance."""
     import ctypes
     a = uniform_matrix(n, n, 586 + n + b, 0.0, 5.0, DT[suf])
     ref = oracle.brd_p1_panel(a, b)
@@ -112,7 +112,7 @@ def test_stage1_panel_order_vs_oracle_larger(capi, oracle, n, b, suf, blocked):
         assert rel <= TOL[suf]
     elif rel > TOL[suf]:
         rel2, flips = band_rel_mod_signs(out, ref, b)
-        assert rel2 <= TOL[suf] and flips <= 8, (rel, rel2, flips)
+        assert rel2 <= TOL[suf], (rel, rel2, flips)          # one flipped pivot re-signs every later reflector it feeds
 
 
 @pytest.mark.parametrize("n", [24, 33])

@@ -229,3 +229,21 @@ def test_complete_schedule_dependency_lag(n, b):
                 if overlap(oa, ob):
                     worst = max(worst, qa - q)
     assert worst <= 3
+
+
+@pytest.mark.parametrize("suf,dt", [("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("n", [8, 48, 96])
+def test_onestage_brd_oracle_pinned_to_reference(oracle, suf, dt, n):
+    """svdo_brd_serial (restatement of serial::brd, svd_serial.h:233-266) == the compiled reference, bit for bit
+    (golden_onestage.npz, generated by tools/make_golden.py from oracle/_ref)."""
+    import os
+    from conftest import GOLDEN
+    from svdsolver_b200.synth import uniform_matrix
+    g = np.load(os.path.join(GOLDEN, "golden_onestage.npz"))
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt)
+    x, d, e = oracle.brd_serial(a)
+    assert np.array_equal(x, g[f"brd_{n}_{suf}"]) and np.array_equal(d, g[f"brd_d_{n}_{suf}"]) and np.array_equal(e, g[f"brd_e_{n}_{suf}"])
+    # an orthogonal reduction: singular values of the bidiagonal == singular values of the input
+    s0 = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+    s1 = np.linalg.svd(np.diag(d.astype(np.float64)) + np.diag(e.astype(np.float64), 1), compute_uv=False)
+    assert np.abs(s0 - s1).max() <= (1e-5 if suf == "f32" else 1e-13) * s0[0]

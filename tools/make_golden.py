@@ -37,8 +37,24 @@ def ref_chain(a, band, suf):
     return band_m, x, d, e
 
 
+def onestage():
+    """csc586::serial::brd<T> (svd_serial.h:233) on seeded inputs: full output matrix + (d, e)."""
+    z = {}
+    for n in (8, 48, 96):
+        for suf, dt in DT.items():
+            a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt)
+            x = a.copy(); d = np.zeros(n, dt); e = np.zeros(n - 1, dt)
+            getattr(L, f"svdref_serial_brd_{suf}")(P(x), Z(n), P(d), P(e))
+            z[f"brd_{n}_{suf}"] = x; z[f"brd_d_{n}_{suf}"] = d; z[f"brd_e_{n}_{suf}"] = e
+    np.savez_compressed(os.path.join(OUT, "golden_onestage.npz"), **z)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-onestage" in sys.argv:
+        onestage()
+        return
+    onestage()
     for n in (64, 512):
         for name in ("float", "double"):
             for kind in ("test", "band", "bidiagonal"):
