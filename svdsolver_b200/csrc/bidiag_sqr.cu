@@ -42,19 +42,19 @@ __device__ void warp_sort_desc(T* v, int npad) {
 template <typename T, bool kSmem>
 __global__ void __launch_bounds__(32, 1)
 bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict__ sigma, T* __restrict__ sortbuf, int npad,
-                  long long* __restrict__ info) {
+                  long long* __restrict__ info, double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double z2[4 * kLanes];
     __shared__ double mu_s[kLanes];
     __shared__ int bot_s;
-    T* d = kSmem ? reinterpret_cast<T*>(smem_raw) : d_g;
-    T* e = kSmem ? d + n : e_g;
+    // the iteration runs on a DOUBLE copy of the bidiagonal for both element types (float storage would round d / e after
+    // each of the ~3 n sweeps): shared memory up to n = 12800, a global workspace above
+    double* d = kSmem ? reinterpret_cast<double*>(smem_raw) : ws;
+    double* e = d + n;
     const int lane = threadIdx.x;
-    if (kSmem) {
-        for (int i = lane; i < n; i += 32) d[i] = d_g[i];
-        for (int i = lane; i < n - 1; i += 32) e[i] = e_g[i];
-        __syncwarp();
-    }
+    for (int i = lane; i < n; i += 32) d[i] = (double)d_g[i];
+    for (int i = lane; i < n - 1; i += 32) e[i] = (double)e_g[i];
+    __syncwarp();
     long long sweeps = 0, passes = 0;
     const long long max_sweeps = 60LL * n + 1000;
     int hi = n - 1, status = 0;
@@ -65,9 +65,9 @@ bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict
             const int i = hi - 1 - lane;
             bool neg = true;
             if (i >= 0) {
-                const T ei = e[i];
-                neg = (ei == (T)0) || sqr_negligible(ei, d[i], d[i + 1], kTol);
-                if (neg && ei != (T)0) e[i] = (T)0;
+                const double ei = e[i];
+                neg = (ei == 0.0) || sqr_negligible(ei, d[i], d[i + 1], kTol);
+                if (neg && ei != 0.0) e[i] = 0.0;
             }
             const unsigned m = __ballot_sync(0xffffffffu, !neg && i >= 0);
             if (m != 0u) { hi -= __ffs(m) - 1; break; }
@@ -81,9 +81,9 @@ bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict
             const int i = lo - 1 - lane;
             bool neg = true;
             if (i >= 0) {
-                const T ei = e[i];
-                neg = (ei == (T)0) || sqr_negligible(ei, d[i], d[i + 1], kTol);
-                if (neg && ei != (T)0) e[i] = (T)0;
+                const double ei = e[i];
+                neg = (ei == 0.0) || sqr_negligible(ei, d[i], d[i + 1], kTol);
+                if (neg && ei != 0.0) e[i] = 0.0;
             }
             const unsigned m = __ballot_sync(0xffffffffu, neg || i < 0);
             if (m != 0u) { lo -= __ffs(m) - 1; break; }
@@ -94,15 +94,15 @@ bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict
         const int nd = hi - lo + 1;
         // ---- zero diagonal entries split the window ------------------------------------------------------------------------
         double dmax = 0.0;
-        for (int i = lo + lane; i <= hi; i += 32) dmax = fmax(dmax, fabs((double)d[i]));
+        for (int i = lo + lane; i <= hi; i += 32) dmax = fmax(dmax, fabs(d[i]));
         for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
         bool zero_here = false;
-        for (int i = lo + lane; i <= hi; i += 32) zero_here |= fabs((double)d[i]) <= kTol * dmax;
+        for (int i = lo + lane; i <= hi; i += 32) zero_here |= fabs(d[i]) <= kTol * dmax;
         if (__any_sync(0xffffffffu, zero_here)) {
             if (lane == 0) {
                 for (int i = lo; i <= hi; ++i)
-                    if (fabs((double)d[i]) <= kTol * dmax) {
-                        d[i] = (T)0;
+                    if (fabs(d[i]) <= kTol * dmax) {
+                        d[i] = 0.0;
                         if (i < hi) sqr_chase_zero_row(d, e, i, hi);
                         else sqr_chase_zero_col(d, e, lo, hi);
                     }
@@ -135,11 +135,11 @@ bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict
                 if (pos >= bot || bot <= lo) {
                     running = false;                           // the window ended above this sweep's next position
                 } else {
-                    if (pos == lo) car = sqr_start((double)d[lo], (double)e[lo], mu_s[lane]);
+                    if (pos == lo) car = sqr_start(d[lo], e[lo], mu_s[lane]);
                     sqr_position(d, e, pos, lo, bot, car);
                     if (pos == bot - 1) {                      // finished: deflate the bottom entry if it converged
                         running = false;
-                        if (sqr_negligible(e[bot - 1], d[bot - 1], d[bot], kTol)) { e[bot - 1] = (T)0; bot_s = bot - 1; }
+                        if (sqr_negligible(e[bot - 1], d[bot - 1], d[bot], kTol)) { e[bot - 1] = 0.0; bot_s = bot - 1; }
                     }
                 }
             }
@@ -149,14 +149,12 @@ bidiag_sqr_kernel(T* __restrict__ d_g, T* __restrict__ e_g, int n, T* __restrict
         ++passes;
     }
     __syncwarp();
-    for (int i = lane; i < npad; i += 32) sortbuf[i] = (i < n) ? (T)fabs((double)d[i]) : (T)-1;
+    for (int i = lane; i < npad; i += 32) sortbuf[i] = (i < n) ? (T)fabs(d[i]) : (T)-1;
     __syncwarp();
     warp_sort_desc<T>(sortbuf, npad);
     for (int i = lane; i < n; i += 32) sigma[i] = sortbuf[i];
-    if (kSmem) {
-        for (int i = lane; i < n; i += 32) d_g[i] = d[i];
-        for (int i = lane; i < n - 1; i += 32) e_g[i] = e[i];
-    }
+    for (int i = lane; i < n; i += 32) d_g[i] = (T)d[i];
+    for (int i = lane; i < n - 1; i += 32) e_g[i] = (T)e[i];
     if (lane == 0 && info) { info[0] = sweeps; info[1] = status; info[2] = passes; }
 }
 
@@ -170,15 +168,22 @@ int bidiag_sqr(Ctx* c, T* d, T* e, size_t n, T* sigma) {
     while ((size_t)npad < n) npad <<= 1;
     if (c->wpart_elems < (size_t)npad) return SVDB200_E_CAPACITY;
     T* sortbuf = reinterpret_cast<T*>(c->wpart);
-    const size_t smem = 2 * n * sizeof(T);
+    const size_t smem = 2 * n * sizeof(double);
     int ni = (int)n;
     if (smem <= 200 * 1024) {
         auto kern = bidiag_sqr_kernel<T, true>;
         SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<1, 32, smem, c->stream>>>(d, e, ni, sigma, sortbuf, npad, c->qr_info);
+        kern<<<1, 32, smem, c->stream>>>(d, e, ni, sigma, sortbuf, npad, c->qr_info, (double*)nullptr);
     } else {
+        if (c->bis_ws_elems < 2 * n + 24) {                      // double workspace shared with the bisection solver
+            if (c->bis_ws) cudaFree(c->bis_ws);
+            c->bis_ws = nullptr; c->bis_ws_elems = 0;
+            const size_t want = 2 * c->max_n + 24;
+            SVDB_CHECK(c, cudaMalloc(&c->bis_ws, sizeof(double) * want));
+            c->bis_ws_elems = want;
+        }
         auto kern = bidiag_sqr_kernel<T, false>;
-        kern<<<1, 32, 0, c->stream>>>(d, e, ni, sigma, sortbuf, npad, c->qr_info);
+        kern<<<1, 32, 0, c->stream>>>(d, e, ni, sigma, sortbuf, npad, c->qr_info, reinterpret_cast<double*>(c->bis_ws));
     }
     SVDB_CHECK(c, cudaGetLastError());
     c->launches++;

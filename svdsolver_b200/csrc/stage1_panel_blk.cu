@@ -233,13 +233,15 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 for (int ii = 0; ii < CH; ++ii) {
                     const int i = i0 + ii, rl = w + kWarps * i;
                     const bool islo = rl < R && (r0 + rl) >= j + C;          // warp-uniform
-                    const T lo = islo ? (T)1 : (T)0;
+#pragma unroll
+                    for (int p = 0; p < C; ++p) x[ii][p] = islo ? x[ii][p] : (T)0;   // selects, not multiplies (FP64 pipe)
 #pragma unroll
                     for (int u = 0; u < CPL; ++u) {
-                        T v = (islo && fin[u]) ? (T)0 : a[i][u];
+                        // two partial sums: half the length of the dependent FMA chain
+                        T v0 = (islo && fin[u]) ? (T)0 : a[i][u], v1 = (T)0;
 #pragma unroll
-                        for (int p = 0; p < C; ++p) v += (lo * x[ii][p]) * K[p][u];
-                        a[i][u] = v;
+                        for (int p = 0; p < C; p += 2) { v0 += x[ii][p] * K[p][u]; v1 += x[ii][p + 1] * K[p + 1][u]; }
+                        a[i][u] = v0 + v1;
                     }
                 }
             }
@@ -268,10 +270,10 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                         }
                     }
                     const int i = i0 + ii, rl = w + kWarps * i;
-                    const T lo2 = (rl < R && (r0 + rl) >= jn + C) ? (T)1 : (T)0;
+                    const bool lo2 = rl < R && (r0 + rl) >= jn + C;
 #pragma unroll
                     for (int p = 0; p < C; ++p) {
-                        const T yv = y[p] * (lo2 * ymask[p]);
+                        const T yv = (lo2 && ymask[p] != (T)0) ? y[p] : (T)0;
 #pragma unroll
                         for (int u = 0; u < CPL; ++u) accf[p][u] += yv * a[i][u];
                     }
@@ -579,6 +581,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     // ---- epilogue --------------------------------------------------------------------------------------------------
     if (G > 1) cg::this_cluster().sync();                 // nobody pushes words into the staging area any more
     else __syncthreads();
+    BLK_TICK(10);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int rl = w + kWarps * i;
@@ -605,6 +608,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     // sits in Ps (odd leading dimension: conflict-free), every T entry is a broadcast load shared by the 32 rows of a warp;
     // no dependent chain (the per-column kernels solve a triangular system per row here).
     __syncthreads();
+    BLK_TICK(11);
     for (int rl = tid; rl < R; rl += nt) {                // explicit unit diagonal, zeros above it (rows of the top block only)
         const int row = r0 + rl;
         if (row < b) {
@@ -663,6 +667,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         }
     }
     __syncthreads();
+    BLK_TICK(12);
     if (!kTrans) {
         if (in2d)
             for (int rl = tyy; rl < R; rl += rgroups) V2[(size_t)(r0 + rl) * b + tx] = Ps[rl * ld + tx];

@@ -39,12 +39,14 @@ for k in range(0, len(args), 3):
         p = h.get_profile()["panel"]
         capi.lib().svdb200_debug_panel_blk_timing(out)
         rounds, panels = max(out[8], 1), max(out[9], 1)
-        names = ["load + first dot products", "publish psum + sync", "all-reduce", "algebra (8 Householder steps)", "pass (update + next dots)", "epilogue"]
-        tot = sum(out[i] for i in range(6))
+        names = ["load + first dot products", "publish psum + sync", "all-reduce", "algebra (8 Householder steps)", "pass (update + next dots)", "epilogue: V2 stores"]
+        tot = sum(out[i] for i in range(6)) + sum(out[i] for i in (10, 11, 12))
         print(f"n={n} band={b} {suf}: {panels} panels, {rounds} rounds ({rounds / panels:.2f} per panel; band/8 = {b // 8}), "
               f"panel class {p['ms']:.2f} ms = {p['ms'] / panels * 1e3:.1f} us per panel; CTA-0 cycles per panel {tot / panels:.0f}")
         for i, nm in enumerate(names):
             per = out[i] / (panels if i in (0, 5) else rounds)
             print(f"    {nm:32s} {100.0 * out[i] / tot:5.1f}%   {per:9.0f} cycles per {'panel' if i in (0, 5) else 'round'}")
+        for i, nm in ((10, "epilogue: last T block + cluster sync"), (11, "epilogue: stage rows, V / R stores"), (12, "epilogue: V2 = V S^T")):
+            print(f"    {nm:40s} {100.0 * out[i] / tot:5.1f}%   {out[i] / panels:9.0f} cycles per panel")
     del a
     torch.cuda.empty_cache()
