@@ -223,6 +223,13 @@ int svdb200_rank_update_dev_f64(svdb200_handle h, double* c, size_t ldc, size_t 
 int svdb200_gemm_nn_dev_f32(svdb200_handle h, const float* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const float* ut, float* w);
 int svdb200_gemm_nn_dev_f64(svdb200_handle h, const double* c, size_t ldc, size_t mrows, size_t ncols, size_t b, const double* ut, double* w);
 
+/* One stage-1 panel on its own (qr / lq of svd_parallel.h:133-226 in the panel order of svd_cuda_2.cu:881 / 959): the
+ * m x b panel at a (leading dimension lda; trans != 0: the b x m ROW panel, factorised as its transpose) is overwritten
+ * by R (zeros below the diagonal); v receives V (m x b, unit diagonal explicit), v2 = V S^T (m x b; trans: b x m) with
+ * Q = I + V S V^T.  Exposed for kernel-level parity tests and timing of tall panels; m <= max_n, b <= band of the handle. */
+int svdb200_panel_factor_dev_f32(svdb200_handle h, float* a_dev, size_t lda, size_t m, size_t b, int trans, float* v_dev, float* v2_dev);
+int svdb200_panel_factor_dev_f64(svdb200_handle h, double* a_dev, size_t lda, size_t m, size_t b, int trans, double* v_dev, double* v2_dev);
+
 /* ---- Multi-GPU stage 1 (BASELINE config 4): 1-D block-cyclic over columns, one process per GPU.
  * nccl_unique_id: the 128-byte ncclUniqueId produced by svdb200_dist_unique_id on rank 0 and
  * broadcast by the launcher (torch.distributed / MPI / a file).  a_local holds this rank's block

@@ -243,6 +243,10 @@ class Handle:
     def rank_update_dev(self, c_ptr, ldc, mrows, ncols, b, p_ptr, q_ptr, ldq):
         self._check(self._fn("rank_update_dev")(self.h, _p(c_ptr), Z(ldc), Z(mrows), Z(ncols), Z(b), _p(p_ptr), _p(q_ptr), Z(ldq)))
 
+    def panel_factor_dev(self, a_ptr, lda, m, b, trans, v_ptr, v2_ptr):
+        """one stage-1 panel (QR of the m x b column panel, or LQ of the b x m row panel when trans)"""
+        self._check(self._fn("panel_factor_dev")(self.h, _p(a_ptr), Z(lda), Z(m), Z(b), ctypes.c_int(1 if trans else 0), _p(v_ptr), _p(v2_ptr)))
+
     def last_timings(self):
         v = [ctypes.c_double(0) for _ in range(5)]
         self._check(lib().svdb200_last_timings(self.h, *[ctypes.byref(x) for x in v]))

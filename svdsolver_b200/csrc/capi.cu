@@ -8,6 +8,7 @@
 using namespace svdb200;
 
 namespace svdb200 {
+template <typename T, bool kTrans> int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
 namespace {
 
 // ---- small utility kernels ------------------------------------------------------------------------
@@ -926,6 +927,12 @@ int svdb200_synchronize(svdb200_handle h) {
         if (!a || what <= 0 || what > 7 || ((what & 4) && !sigma)) return SVDB200_E_ARG;                                 \
         SVDB_TRY(check_square(c, n, n, band, dtype_of<T>()));                                                            \
         return batched_chain<T>(c, a, count, n, band, what, d, e, sigma);                                                \
+    }                                                                                                                    \
+    int svdb200_panel_factor_dev_##S(svdb200_handle h, T* a, size_t lda, size_t m, size_t b, int trans, T* v, T* v2) {   \
+        SVDB_ENTER(T)                                                                                                    \
+        if (!a || !v || !v2 || m == 0 || b == 0 || b > c->band || m > c->max_n) return SVDB200_E_ARG;                    \
+        return trans ? launch_panel_public<T, true>(c, a, lda, (int)m, (int)b, v, v2, c->stream)                        \
+                     : launch_panel_public<T, false>(c, a, lda, (int)m, (int)b, v, v2, c->stream);                       \
     }                                                                                                                    \
     int svdb200_mse_##S(svdb200_handle h, const T* a, const T* b, size_t n, size_t band, T* out) {                       \
         SVDB_ENTER(T)                                                                                                    \

@@ -1,4 +1,5 @@
-// Blocked register-resident panel factorisation: ONE exchange per sub-panel of C = 8 columns instead of one per column.
+// Blocked panel factorisation, slice resident in shared memory: ONE exchange per sub-panel of C = 8 columns instead of one
+// per column.
 // Same algorithm, sign convention (svd_serial.h:194-201: H x = -sign(x0) ||x|| e1) and outputs as panel_reg_kernel /
 // panel_factor_kernel (R or L in A with exact zeros below the diagonal, V with explicit unit diagonal, V2 = V S^T with
 // S = -T of the compact-WY form, svd_parallel.h:97-113) -- those kernels exchange the dot products of ONE pivot column
@@ -70,47 +71,47 @@ __host__ __device__ inline BlkShape blk_shape(int b, int CS, int NC) {
     return s;
 }
 
-// Shared-memory plan (bytes).  The staging area holds the transposed load / epilogue copy of the slice (Ps) outside the
-// column loop and the exchange words + per-warp dot products inside it.
+// Shared-memory plan (bytes).  The slice of the panel (rows x (b+1)) stays in shared memory for the whole factorisation
+// (an earlier version kept it in registers: its fully unrolled row loops made the kernel instruction-fetch bound --
+// ncu: 4 "no instruction" stall cycles per issued instruction -- and needed one instantiation per slice height).
 struct BlkSmem {
-    size_t stage, psum_off, total;
+    size_t ps, exch_off, psum_off, rest_off, total;
 };
-__host__ __device__ inline BlkSmem blk_smem(int rows, int b, size_t esz, const BlkShape& sh) {
+__host__ __device__ inline BlkSmem blk_smem(int rows, int b, size_t esz, const BlkShape& sh, int dbl) {
     const size_t CB = (size_t)kC * b;
     BlkSmem m;
-    const size_t ps = (size_t)rows * (b + 1) * esz;
-    const size_t exch = (sh.CS * sh.NC > 1) ? sh.exch_bytes : 0;
-    m.psum_off = (exch + 15) & ~(size_t)15;
-    const size_t loop = m.psum_off + (size_t)kWarps * CB * 8;
-    m.stage = ((ps > loop ? ps : loop) + 15) & ~(size_t)15;
+    m.ps = (((size_t)rows * (b + 1) * esz) + 15) & ~(size_t)15;
+    const size_t exch = (sh.CS * sh.NC > 1) ? (dbl ? sh.exch_bytes : sh.exch_bytes / 2) : 0;
+    m.exch_off = m.ps;
+    m.psum_off = m.exch_off + ((exch + 15) & ~(size_t)15);
+    m.rest_off = m.psum_off + 4 * CB * 8;                  // 4 buffers: warps w and w+4 share one (two write phases)
     // doubles: red (L) + topS (CB) + Cs (CB) + srow (b) + fas (b);
-    // elements: Tt (b*b) + Gp (2*b*8) + Zs (b*8) + T22s (64) + taus (b) + Kc + TopF (CB each) + xs (kWarps * 256); ctl
-    m.total = m.stage + (2 * CB + CB + CB + 2 * (size_t)b) * 8 +
-              ((size_t)b * b + 24 * (size_t)b + 64 + b + 2 * CB + (size_t)kWarps * 256) * esz + 64;
+    // elements: Tt (b*b) + Gp (2*b*8) + Zs (b*8) + T22s (64) + taus (b) + Kc + TopF (CB each); ctl
+    m.total = m.rest_off + (2 * CB + CB + CB + 2 * (size_t)b) * 8 + ((size_t)b * b + 24 * (size_t)b + 64 + b + 2 * CB) * esz + 64;
     return m;
 }
 
-template <typename T, bool kTrans, int RPT, int CPL>
+template <typename T, bool kTrans, int CPL>
 __global__ void __launch_bounds__(kThreads, 1)
 panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, char* __restrict__ gbuf, int NC,
-                 unsigned epoch) {
+                 unsigned epoch, int ROWS, int dbl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kFloat = sizeof(T) == 4;
-    constexpr int ROWS = RPT * kWarps, C = kC, CH = kFloat ? (RPT < 8 ? RPT : 8) : (RPT < 4 ? RPT : 4);   // rows per staging chunk
+    constexpr int C = kC;
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31, w = tid >> 5;
     const int G = gridDim.x, g = blockIdx.x;
     const int CS = G / NC, cl = g / CS, crank = g - cl * CS;
     const BlkShape sh = blk_shape(b, CS, NC);
-    const BlkSmem plan = blk_smem(ROWS, b, sizeof(T), sh);
+    const BlkSmem plan = blk_smem(ROWS, b, sizeof(T), sh, dbl);
     const int L = sh.L, SL = sh.SL, CB = C * b;
     const int r0 = g * ROWS;
     const int R = max(0, min(ROWS, m - r0));
     const int ld = b + 1;
     // ---- shared memory ----------------------------------------------------------------------------------
-    unsigned char* stage = smem_raw;
-    T* Ps = reinterpret_cast<T*>(stage);                  // ROWS x ld (outside the column loop)
-    double* psum = reinterpret_cast<double*>(stage + plan.psum_off);   // kWarps x CB (inside the loop; reused for slice partials)
-    double* red = reinterpret_cast<double*>(stage + plan.stage);       // L : reduced D (CB), then Top (CB) -- the algebra works on Top in place
+    T* Ps = reinterpret_cast<T*>(smem_raw);               // ROWS x ld : the slice, resident for the whole factorisation
+    unsigned char* exch = smem_raw + plan.exch_off;       // exchange words
+    double* psum = reinterpret_cast<double*>(smem_raw + plan.psum_off);   // 4 x CB per-warp-pair dot products (reused for slice partials)
+    double* red = reinterpret_cast<double*>(smem_raw + plan.rest_off);    // L : reduced D (CB), then Top (CB) -- the algebra works on Top in place
     double* topS = red + L;                               // CB : this CTA's rows among the C top rows (zeros elsewhere)
     double* Cs = topS + CB;                               // CB : coefficients Cm[p][col] of the algebra
     double* srow = Cs + CB;                               // b  : row i of S (dots of the pivot column's lo part with every column)
@@ -122,10 +123,10 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     T* taus = T22s + 64;                                  // b
     T* Kc = taus + b;                                     // CB : pass coefficients per column
     T* TopF = Kc + CB;                                    // CB : final top rows of the sub-panel
-    T* xs = TopF + CB;                                    // kWarps x 2 (chunk parity) x 2 (x / y) x CH x 8 : broadcast staging
-    int* ctl = reinterpret_cast<int*>(xs + kWarps * 256);  // [0] = C_eff
-    const unsigned l1_base = smem_addr(stage);
-    const unsigned in_bytes = (unsigned)(2 * CS * SL * 16);
+    int* ctl = reinterpret_cast<int*>(TopF + CB);         // [0] = C_eff
+    const unsigned l1_base = smem_addr(exch);
+    const int npar = dbl ? 2 : 1;
+    const unsigned in_bytes = (unsigned)(npar * CS * SL * 16);
     auto in_off = [&](int par, int src, int e) { return (unsigned)(((par * CS + src) * SL + e) * 16); };
     auto out_off = [&](int par, int idx) { return in_bytes + (unsigned)((par * L + idx) * 16); };
 
@@ -136,32 +137,19 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     const int tx = tid % b, tyy = tid / b, rgroups = max(1, nt / b);
     const bool in2d = tyy < rgroups;
 
-    // ---- load --------------------------------------------------------------------------------------------
-    T a[RPT][CPL];
+    // ---- load the slice ------------------------------------------------------------------------------------------
     if (!kTrans) {
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int rl = w + kWarps * i;
-#pragma unroll
-            for (int u = 0; u < CPL; ++u) a[i][u] = (rl < R && valid[u]) ? A[(size_t)(r0 + rl) * lda + cu[u]] : (T)0;
-        }
+        if (in2d)
+            for (int rl = tyy; rl < R; rl += rgroups) Ps[rl * ld + tx] = A[(size_t)(r0 + rl) * lda + tx];
     } else {
         for (int c = w; c < b; c += kWarps)
             for (int rl = lane; rl < R; rl += 32) Ps[rl * ld + c] = A[(size_t)c * lda + (r0 + rl)];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int rl = w + kWarps * i;
-#pragma unroll
-            for (int u = 0; u < CPL; ++u) a[i][u] = (rl < R && valid[u]) ? Ps[rl * ld + cu[u]] : (T)0;
-        }
     }
-    __syncthreads();                                      // the transposed load is done with Ps
     for (int e = tid; e < b * b; e += nt) Tt[e] = (T)0;
     for (int e = tid; e < CB; e += nt) topS[e] = 0.0;
     if (G > 1) {
-        unsigned* z = reinterpret_cast<unsigned*>(stage);
-        for (int e = tid; e < (int)(sh.exch_bytes / 4); e += nt) z[e] = 0u;
+        unsigned* z = reinterpret_cast<unsigned*>(exch);
+        for (int e = tid; e < (int)((npar * ((size_t)CS * SL + L) * 16) / 4); e += nt) z[e] = 0u;
         cg::this_cluster().sync();                        // every peer's word buffers are cleared before the first push
     } else {
         __syncthreads();
@@ -169,133 +157,79 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
 
     const int kmax = b;                                   // m >= b (checked by the launcher)
     double acc[C][CPL];
-    T* xw = xs + w * 256;
-    // One pass over the local rows.  apply: update with the coefficients of the sub-panel that started at column j and
-    // processed ceff columns; then (always) dot products and top rows for the sub-panel starting at jn.  The C values of a
-    // row that every lane needs (the sub-panel's columns) travel through a per-warp staging buffer in shared memory
-    // (one predicated store + vector broadcast loads per row instead of 2 C shuffles); the loop body has no branches.
+    // One pass over the local rows (warp w: rows w, w+8, ...; lane = column).  apply: update with the coefficients of the
+    // sub-panel that started at column j and processed ceff columns; then (always) dot products and top rows for the
+    // sub-panel starting at jn.  The values of a row that every lane needs (the sub-panel's C columns) are broadcast loads
+    // from the row itself.  Float: the dot products of 8 rows are summed in float, the chunks in double (the norms of
+    // later columns are differences of these sums).
     auto pass = [&](bool apply, int j, int ceff, int jn) {
         T K[C][CPL];
         bool fin[CPL];
-        int pcx[CPL], pcy[CPL];
 #pragma unroll
         for (int u = 0; u < CPL; ++u) {
             fin[u] = apply && cu[u] >= j && cu[u] < j + ceff;
-            pcx[u] = (apply && valid[u] && cu[u] >= j && cu[u] < j + C) ? cu[u] - j : -1;
-            pcy[u] = (valid[u] && cu[u] >= jn && cu[u] < jn + C) ? cu[u] - jn : -1;
 #pragma unroll
             for (int p = 0; p < C; ++p) K[p][u] = (apply && valid[u]) ? Kc[p * b + cu[u]] : (T)0;
+        }
+        T accf[C][CPL];
+#pragma unroll
+        for (int p = 0; p < C; ++p)
+#pragma unroll
+            for (int u = 0; u < CPL; ++u) { acc[p][u] = 0.0; accf[p][u] = (T)0; }
+        const bool more = jn < kmax;
+        int cnt = 0;
+#pragma unroll 1
+        for (int rl = w; rl < R; rl += kWarps) {
+            T* row = Ps + rl * ld;
+            const int grow = r0 + rl;
+            T av[CPL];
+#pragma unroll
+            for (int u = 0; u < CPL; ++u) av[u] = valid[u] ? row[cu[u]] : (T)0;
+            if (apply && grow >= j) {                      // warp-uniform
+                if (grow < j + C) {                        // one of the C top rows: final values from the algebra
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) if (valid[u]) av[u] = TopF[(grow - j) * b + cu[u]];
+                } else {
+                    T x[C];
+#pragma unroll
+                    for (int p = 0; p < C; ++p) x[p] = row[min(j + p, b - 1)];
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) {
+                        T v0 = fin[u] ? (T)0 : av[u], v1 = (T)0;
+#pragma unroll
+                        for (int p = 0; p < C; p += 2) { v0 += x[p] * K[p][u]; v1 += x[p + 1] * K[p + 1][u]; }
+                        av[u] = v0 + v1;
+                    }
+                }
+                __syncwarp();                              // every lane has read the row before it is rewritten
+#pragma unroll
+                for (int u = 0; u < CPL; ++u) if (valid[u]) row[cu[u]] = av[u];
+                __syncwarp();
+            }
+            if (more && grow >= jn) {
+                if (grow < jn + C) {
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) if (valid[u]) topS[(grow - jn) * b + cu[u]] = (double)av[u];
+                } else {
+#pragma unroll
+                    for (int p = 0; p < C; ++p) {
+                        const T yv = (jn + p < kmax) ? row[jn + p] : (T)0;
+#pragma unroll
+                        for (int u = 0; u < CPL; ++u) accf[p][u] += yv * av[u];
+                    }
+                    if (!kFloat || ((++cnt) & 7) == 0) {
+#pragma unroll
+                        for (int p = 0; p < C; ++p)
+#pragma unroll
+                            for (int u = 0; u < CPL; ++u) { acc[p][u] += (double)accf[p][u]; accf[p][u] = (T)0; }
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int p = 0; p < C; ++p)
 #pragma unroll
-            for (int u = 0; u < CPL; ++u) acc[p][u] = 0.0;
-        const bool more = jn < kmax;
-        // rows that sit among the C top rows of the finished sub-panel take their final values from the algebra
-        if (apply) {
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const int rl = w + kWarps * i, t = r0 + rl - j;
-                if (rl < R && t >= 0 && t < C) {
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) if (valid[u]) a[i][u] = TopF[t * b + cu[u]];
-                }
-            }
-        }
-        T ymask[C];
-#pragma unroll
-        for (int p = 0; p < C; ++p) ymask[p] = (more && jn + p < kmax) ? (T)1 : (T)0;
-#pragma unroll
-        for (int i0 = 0; i0 < RPT; i0 += CH) {
-            T* bx = xw + ((i0 / CH) & 1) * 128;           // chunk parity: a buffer is rewritten two __syncwarp()s after its last read
-            T* by = bx + 64;
-            T x[CH][C];
-            if (apply) {
-#pragma unroll
-                for (int ii = 0; ii < CH; ++ii)
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) if (pcx[u] >= 0) bx[ii * 8 + pcx[u]] = a[i0 + ii][u];
-                __syncwarp();
-#pragma unroll
-                for (int ii = 0; ii < CH; ++ii) {
-                    if constexpr (kFloat) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(bx + ii * 8), v1 = *reinterpret_cast<const float4*>(bx + ii * 8 + 4);
-                        x[ii][0] = v0.x; x[ii][1] = v0.y; x[ii][2] = v0.z; x[ii][3] = v0.w; x[ii][4] = v1.x; x[ii][5] = v1.y; x[ii][6] = v1.z; x[ii][7] = v1.w;
-                    } else {
-#pragma unroll
-                        for (int p2 = 0; p2 < 4; ++p2) {
-                            const double2 v = *reinterpret_cast<const double2*>(bx + ii * 8 + 2 * p2);
-                            x[ii][2 * p2] = v.x; x[ii][2 * p2 + 1] = v.y;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int ii = 0; ii < CH; ++ii) {
-                    const int i = i0 + ii, rl = w + kWarps * i;
-                    const bool islo = rl < R && (r0 + rl) >= j + C;          // warp-uniform
-#pragma unroll
-                    for (int p = 0; p < C; ++p) x[ii][p] = islo ? x[ii][p] : (T)0;   // selects, not multiplies (FP64 pipe)
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) {
-                        // two partial sums: half the length of the dependent FMA chain
-                        T v0 = (islo && fin[u]) ? (T)0 : a[i][u], v1 = (T)0;
-#pragma unroll
-                        for (int p = 0; p < C; p += 2) { v0 += x[ii][p] * K[p][u]; v1 += x[ii][p + 1] * K[p + 1][u]; }
-                        a[i][u] = v0 + v1;
-                    }
-                }
-            }
-            if (more) {
-#pragma unroll
-                for (int ii = 0; ii < CH; ++ii)
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) if (pcy[u] >= 0) by[ii * 8 + pcy[u]] = a[i0 + ii][u];
-                __syncwarp();
-                T accf[C][CPL];
-#pragma unroll
-                for (int p = 0; p < C; ++p)
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) accf[p][u] = (T)0;
-#pragma unroll
-                for (int ii = 0; ii < CH; ++ii) {
-                    T y[C];
-                    if constexpr (kFloat) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(by + ii * 8), v1 = *reinterpret_cast<const float4*>(by + ii * 8 + 4);
-                        y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; y[5] = v1.y; y[6] = v1.z; y[7] = v1.w;
-                    } else {
-#pragma unroll
-                        for (int p2 = 0; p2 < 4; ++p2) {
-                            const double2 v = *reinterpret_cast<const double2*>(by + ii * 8 + 2 * p2);
-                            y[2 * p2] = v.x; y[2 * p2 + 1] = v.y;
-                        }
-                    }
-                    const int i = i0 + ii, rl = w + kWarps * i;
-                    const bool lo2 = rl < R && (r0 + rl) >= jn + C;
-#pragma unroll
-                    for (int p = 0; p < C; ++p) {
-                        const T yv = (lo2 && ymask[p] != (T)0) ? y[p] : (T)0;
-#pragma unroll
-                        for (int u = 0; u < CPL; ++u) accf[p][u] += yv * a[i][u];
-                    }
-                }
-                // float: the dot products of a chunk are summed in float, the chunks in double (the norms of later
-                // columns are differences of these sums)
-#pragma unroll
-                for (int p = 0; p < C; ++p)
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) acc[p][u] += (double)accf[p][u];
-            }
-        }
-        if (more) {
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const int rl = w + kWarps * i, t = r0 + rl - jn;
-                if (rl < R && t >= 0 && t < C) {
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) if (valid[u]) topS[t * b + cu[u]] = (double)a[i][u];
-                }
-            }
-        }
+            for (int u = 0; u < CPL; ++u) acc[p][u] += (double)accf[p][u];
     };
 
     // compact-WY T of the sub-panel [jp, jp + ce) from its block of Gram entries Gq (b x 8) and the T of the columns left of
@@ -351,33 +285,46 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
 
     long long tick = SVDB_PANEL_TIMING ? clock64() : 0;
     (void)tick;
-    pass(false, 0, 0, 0);
-    BLK_TICK(0);
-    int j = 0, jprev = 0, ceprev = 0;
+    int j = 0, jprev = 0, ceprev = 0, ceff = 0;
     unsigned round = 0;
-    while (j < kmax) {
-        // ---- publish the per-warp dot products ----------------------------------------------------------------
+    bool first = true;
+    while (true) {
+        // update with the finished sub-panel (none the first time) + dot products of the next one: ONE call site, so the
+        // row loop exists once in the instruction stream
+        pass(!first, j, ceff, j + ceff);
+        if (first) { BLK_TICK(0); } else { BLK_TICK(4); if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[8] += 1; }
+        if (!first) { jprev = j; ceprev = ceff; j += ceff; round += 1; }
+        first = false;
+        if (j >= kmax) break;
+        // ---- publish the per-warp dot products: warps 0-3 write, warps 4-7 add (4 buffers instead of 8) ----------------
+        if (w < 4) {
 #pragma unroll
-        for (int p = 0; p < C; ++p)
+            for (int p = 0; p < C; ++p)
 #pragma unroll
-            for (int u = 0; u < CPL; ++u)
-                if (valid[u]) psum[w * CB + p * b + cu[u]] = acc[p][u];
+                for (int u = 0; u < CPL; ++u)
+                    if (valid[u]) psum[w * CB + p * b + cu[u]] = acc[p][u];
+        }
+        __syncthreads();
+        if (w >= 4) {
+#pragma unroll
+            for (int p = 0; p < C; ++p)
+#pragma unroll
+                for (int u = 0; u < CPL; ++u)
+                    if (valid[u]) psum[(w - 4) * CB + p * b + cu[u]] += acc[p][u];
+        }
         __syncthreads();
         BLK_TICK(1);
         // ---- deterministic all-reduce of [D | Top] -----------------------------------------------------------------
         auto local_val = [&](int idx) -> double {
             if (idx >= CB) return topS[idx - CB];
-            double s = psum[idx];
-#pragma unroll
-            for (int q = 1; q < kWarps; ++q) s += psum[q * CB + idx];
-            return s;
+            return (psum[idx] + psum[CB + idx]) + (psum[2 * CB + idx] + psum[3 * CB + idx]);
         };
         if (G == 1) {
             for (int idx = tid; idx < L; idx += nt) red[idx] = local_val(idx);
             __syncthreads();
         } else {
             const unsigned seq = epoch * 128u + round + 1u;
-            const int par = (int)(round & 1u);
+            const int par = dbl ? (int)(round & 1u) : 0;
             // hop 1 (reduce-scatter): slice q of the vector goes to the CTA of rank q in the cluster
             for (int idx = tid; idx < L; idx += nt) {
                 const double v = local_val(idx);
@@ -411,7 +358,7 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
                 const int idx = crank * SL + e;
                 if (NC > 1) {
                     // level 2: the owners of the same slice in the other clusters exchange their sums through L2
-                    char* gs = gbuf + (size_t)par * NC * L * 16;
+                    char* gs = gbuf + (size_t)(round & 1u) * NC * L * 16;
                     LLWord<double>::store(gs + ((size_t)cl * L + idx) * 16, s, seq);
                     double v[kMaxNC];
                     unsigned pending = (1u << NC) - 1u;
@@ -567,13 +514,8 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
         }
         __syncthreads();
         BLK_TICK(3);
-        const int ceff = ctl[0];
-        pass(true, j, ceff, j + ceff);
-        jprev = j; ceprev = ceff;
-        j += ceff;
-        round += 1;
-        BLK_TICK(4);
-        if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[8] += 1;
+        ceff = ctl[0];
+        if (!dbl && G > 1) cg::this_cluster().sync();     // single-parity exchange buffers: everybody is done with this round's words
     }
     __syncthreads();
     if (w != 0) t_update(jprev, ceprev, Gp + ((round + 1u) & 1u) * (b * 8), tid - 32, nt - 32);   // T of the last sub-panel
@@ -582,15 +524,6 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     if (G > 1) cg::this_cluster().sync();                 // nobody pushes words into the staging area any more
     else __syncthreads();
     BLK_TICK(10);
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-        const int rl = w + kWarps * i;
-        if (rl < R) {
-#pragma unroll
-            for (int u = 0; u < CPL; ++u) if (valid[u]) Ps[rl * ld + cu[u]] = a[i][u];
-        }
-    }
-    __syncthreads();
     if (in2d)
         for (int rl = tyy; rl < R; rl += rgroups) {
             const int row = r0 + rl, c = tx;
@@ -679,10 +612,10 @@ panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V,
     if (SVDB_PANEL_TIMING && blockIdx.x == 0 && threadIdx.x == 0) g_blk_dbg[9] += 1;
 }
 
-template <typename T, bool kTrans, int RPT, int CPL>
-int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream) {
-    constexpr int ROWS = RPT * kWarps;
-    const int G0 = (m + ROWS - 1) / ROWS;
+// rows: rows per CTA (multiple of 8).  returns 0 when launched, 1 when this shape cannot run (caller tries another)
+template <typename T, bool kTrans, int CPL>
+int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream, int rows) {
+    const int G0 = (m + rows - 1) / rows;
     int CS = 1, NC = 1;
     if (G0 > 1) {
         if (!c->cluster_ok) return 1;
@@ -693,10 +626,12 @@ int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
         if (NC > 1 && c->overlap_safe) return 1;
     }
     const BlkShape sh = blk_shape(b, CS, NC);
-    const size_t smem = blk_smem(ROWS, b, sizeof(T), sh).total;
+    int dbl = 1;
+    size_t smem = blk_smem(rows, b, sizeof(T), sh, dbl).total;
+    if (smem > 227 * 1024) { dbl = 0; smem = blk_smem(rows, b, sizeof(T), sh, dbl).total; }   // single-parity exchange words + a cluster barrier per round
     if (smem > 227 * 1024) return 1;
-    auto kern = panel_blk_kernel<T, kTrans, RPT, CPL>;
-    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = panel_blk_kernel<T, kTrans, CPL>;
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (CS > 8) SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * CS);
@@ -712,20 +647,20 @@ int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
     cfg.numAttrs = 1;
     if (NC > 1) {
         // all clusters of a launch wait for each other's words: they must be co-resident
-        static int cache_key[16][3], cache_val[16], cache_n = 0;
-        const int key[3] = {CS, (int)smem, (int)(sizeof(T) * 1000 + RPT * 10 + CPL + (kTrans ? 5 : 0))};
+        static int cache_key[32][3], cache_val[32], cache_n = 0;
+        const int key[3] = {CS, (int)smem, (int)(sizeof(T) * 100 + CPL * 10 + (kTrans ? 5 : 0))};
         int max_clusters = -1;
         for (int q = 0; q < cache_n; ++q)
             if (cache_key[q][0] == key[0] && cache_key[q][1] == key[1] && cache_key[q][2] == key[2]) max_clusters = cache_val[q];
         if (max_clusters < 0) {
             max_clusters = 0;
             if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
-            if (cache_n < 16) { cache_key[cache_n][0] = key[0]; cache_key[cache_n][1] = key[1]; cache_key[cache_n][2] = key[2]; cache_val[cache_n] = max_clusters; ++cache_n; }
+            if (cache_n < 32) { cache_key[cache_n][0] = key[0]; cache_key[cache_n][1] = key[1]; cache_key[cache_n][2] = key[2]; cache_val[cache_n] = max_clusters; ++cache_n; }
         }
         if (NC > max_clusters) return 1;
     }
     char* gbuf = reinterpret_cast<char*>(c->red2);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch, rows, dbl);
     if (e != cudaSuccess) { cudaGetLastError(); return 1; }
     c->launches++;
     return 0;
@@ -744,22 +679,22 @@ int panel_blk_debug_read(long long* out16) {
 template <typename T, bool kTrans>
 int launch_panel_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream) {
     if (b < kC || b > 64 || b % kC != 0 || m < b || !c->red2) return 1;
+    // Rows per CTA: one CTA up to 128 rows; then 64 .. 256 rows with the panel inside ONE cluster (<= 16 CTAs) when that
+    // is possible; taller panels run as several clusters of 256-row CTAs, the tallest (more CTAs than the GPU can keep
+    // co-resident) with up to 512 rows per CTA.  Shapes that fit neither shared memory nor the GPU return 1.
     const int maxcs = c->cluster_ok > 0 ? c->cluster_ok : 1;
-    // rows per CTA = 8 * RPT: one CTA up to 128 rows, then the smallest slice that keeps the panel inside one cluster
-    auto fits = [&](int rpt) { return (m + 8 * rpt - 1) / (8 * rpt) <= (m <= 128 ? 1 : maxcs); };
-    if (b <= 32) {
-        if (fits(8)) return launch_blk<T, kTrans, 8, 1>(c, a, lda, m, b, V, V2, stream);
-        if (fits(16)) return launch_blk<T, kTrans, 16, 1>(c, a, lda, m, b, V, V2, stream);
-        if (sizeof(T) == 8 || fits(32)) return launch_blk<T, kTrans, 32, 1>(c, a, lda, m, b, V, V2, stream);
-        return launch_blk<float, kTrans, 64, 1>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
+    auto run = [&](int rows) -> int {
+        if (b <= 32) return launch_blk<T, kTrans, 1>(c, a, lda, m, b, V, V2, stream, rows);
+        return launch_blk<T, kTrans, 2>(c, a, lda, m, b, V, V2, stream, rows);
+    };
+    if (m <= 128) return run((m + 7) / 8 * 8);
+    for (int rows = 64; rows <= 512; rows += 32)
+        if ((m + rows - 1) / rows <= maxcs) { const int st = run(rows); if (st != 1) return st; }
+    for (int rows = 64; rows <= 512; rows += 32) {
+        const int G0 = (m + rows - 1) / rows;
+        if (G0 <= 8 * maxcs && G0 <= c->num_sms - 20) { const int st = run(rows); if (st != 1) return st; }
     }
-    if (fits(8)) return launch_blk<T, kTrans, 8, 2>(c, a, lda, m, b, V, V2, stream);
-    if (sizeof(T) == 8 || fits(16)) return launch_blk<T, kTrans, 16, 2>(c, a, lda, m, b, V, V2, stream);
-    // float, band 64: 256 rows per CTA (several clusters beyond 4096 rows) as long as the CTAs fit the GPU; 512 rows per CTA
-    // (128 registers of panel per thread: spills) only for the 65536-row panels of the multi-GPU configuration
-    if (fits(32) || (!c->overlap_safe && (m + 255) / 256 <= c->num_sms - 4))
-        return launch_blk<float, kTrans, 32, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
-    return launch_blk<float, kTrans, 64, 2>(c, (float*)a, lda, m, b, (float*)V, (float*)V2, stream);
+    return 1;
 }
 template int launch_panel_blk<float, false>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t);
 template int launch_panel_blk<float, true>(Ctx*, float*, size_t, int, int, float*, float*, cudaStream_t);
