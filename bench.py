@@ -419,7 +419,8 @@ def dist_stage1_config(args, capi, torch, dist, stream, dev, local_rank, rank, w
     try:
         uid = D.exchange_unique_id(rank, world)
         out.update(one(world, rank, uid, 2))
-        out["collectives"] = "ncclBroadcast([V | V S^T]), ncclAllGather(row panel), ncclAllReduce(W)" if world > 1 else "none (one rank)"
+        out["collectives"] = ("per block step: ncclBroadcast([V | V S^T]) of the QR panel, ncclAllReduce([Gram | top block], 50 KB, double) of the "
+                              "distributed LQ panel, ncclAllReduce(W)") if world > 1 else "none (one rank)"
         if world > 1:
             t1 = torch.zeros(1, device=dev, dtype=torch.float64)
             if rank == 0:

@@ -187,10 +187,19 @@ int svdb200_set_tc05(svdb200_handle h, int mode, long long min_elems);
  * the same windows and arithmetic, continued until they are empty; orthogonally equivalent to the input (sigma to
  * round-off).  Use 0 for parity with the reference, 1 when the singular values themselves matter. */
 int svdb200_set_stage2_schedule(svdb200_handle h, int mode);
-/* Stage-1 panel kernel: 1 (default) = blocked kernel, one exchange between the CTAs per sub-panel of 8 columns
- * (band a multiple of 8, <= 64); 0 = the per-column kernels (one exchange per column).  Same results to round-off. */
-int svdb200_set_panel_kernel(svdb200_handle h, int blocked);
+/* Stage-1 panel kernel (replaces qr_cuda / lq_cuda, svd_cuda_2.cu:881/959): 2 (default) = Cholesky-QR with reconstructed
+ * Householder vectors (two passes over the panel, no exchange between CTAs; band 8/16/32/64, panel height >= 2 band) with
+ * the blocked kernel as the fallback for ill-conditioned panels; 1 = blocked kernel, one exchange between the CTAs per
+ * sub-panel of 8 columns (band a multiple of 8, <= 64); 0 = the per-column kernels (one exchange per column).  Same
+ * factorisation (sign rule of svd_serial.h:194-201), results equal to round-off. */
+int svdb200_set_panel_kernel(svdb200_handle h, int kind);
+/* Smallest pivot ratio min_j R_jj^2 / G_jj the Cholesky-QR panel accepts (default 1e-3); panels below are redone by the
+ * exchange-based kernels inside the same call.  svdb200_chol_fallback_count: how often that happened on this handle
+ * (synchronises the handle's streams). */
+int svdb200_set_chol_guard(svdb200_handle h, double guard);
+int svdb200_chol_fallback_count(svdb200_handle h, long long* count);
 int svdb200_debug_panel_blk_timing(long long* out16);
+int svdb200_debug_panel_chol_timing(long long* out16);
 /* Debug: per-phase cycle counters of the register panel kernel (all zero unless built with -DSVDB_PANEL_TIMING=1). */
 int svdb200_debug_panel_timing(long long* out16);
 /* same for the stage-2 kernel (-DSVDB_S2_TIMING=1): RIGHT ops of CTA 1 */
@@ -255,6 +264,13 @@ int svdb200_dist_svdvals_dev_f32(svdb200_dist_handle h, float* a_local_dev, floa
 int svdb200_dist_svdvals_dev_f64(svdb200_dist_handle h, double* a_local_dev, double* sigma_dev);
 /* run-time switches of the handle's single-GPU stages (see svdb200_set_stage2_schedule / _qr_method / _tc05); -1 keeps */
 int svdb200_dist_configure(svdb200_dist_handle h, int stage2_schedule, int qr_method, int tc05_mode);
+/* LQ (row) panels of the distributed stage 1: 1 (default) = every rank forms the Gram matrix of its own columns of the
+ * row panel, one all-reduce of band^2-sized data, identical band x band algebra on every rank (Cholesky-QR with
+ * reconstructed Householder vectors); row panels whose pivot ratio falls below the guard are redone through the other
+ * path (svdb200_dist_lq_fallback_count says how many); 0 = all-gather of the row panel, factorised redundantly on every
+ * rank by the single-GPU panel kernels.  Same factorisation, results equal to round-off. */
+int svdb200_dist_configure_panels(svdb200_dist_handle h, int lq_distributed);
+long long svdb200_dist_lq_fallback_count(svdb200_dist_handle h);
 int svdb200_dist_set_stream(svdb200_dist_handle h, void* cuda_stream);
 long long svdb200_dist_launch_count(svdb200_dist_handle h);
 

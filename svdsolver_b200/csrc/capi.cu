@@ -192,6 +192,9 @@ static void inherit_settings(const Ctx* c, Ctx* s) {
     s->use_tc05 = c->use_tc05; s->tc05_min_elems = c->tc05_min_elems;
     s->lookahead = c->lookahead; s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
     s->panel_blk = c->panel_blk;
+    s->panel_chol = c->panel_chol;
+    s->lookahead_reserve = c->lookahead_reserve;
+    s->chol_guard = c->chol_guard;
 }
 
 // Small matrices (n <= 1024, band <= 64): every kernel of the path runs ONCE PER STEP FOR THE WHOLE BATCH -- a
@@ -722,6 +725,16 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
     SVDB_CREATE_CHECK(cudaMemset(c->red, 0, es * 2 * (kMaxPanelCtas + 1) * (2 * band + 8)));   // flag-stamped words start unset
     SVDB_CREATE_CHECK(cudaMalloc(&c->red2, 512 * 1024));
     SVDB_CREATE_CHECK(cudaMemset(c->red2, 0, 512 * 1024));
+    SVDB_CREATE_CHECK(cudaMalloc(&c->chol_ws, 1 << 20));
+    SVDB_CREATE_CHECK(cudaMemset(c->chol_ws, 0, 1 << 20));
+    {
+        const char* rs = getenv("SVDB200_RESERVE_SMS");
+        if (rs && rs[0]) c->lookahead_reserve = atoi(rs);
+        const char* pc = getenv("SVDB200_PANEL_CHOL");
+        if (pc && pc[0] == '0') c->panel_chol = 0;
+        const char* pg = getenv("SVDB200_CHOL_GUARD");
+        if (pg && pg[0]) c->chol_guard = atof(pg);
+    }
     SVDB_CREATE_CHECK(cudaMalloc(&c->bar, 64));
     SVDB_CREATE_CHECK(cudaMemset(c->bar, 0, 64));
     SVDB_CREATE_CHECK(cudaMalloc(&c->prog, sizeof(int) * (max_n + 8)));
@@ -744,7 +757,7 @@ int svdb200_destroy(svdb200_handle h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (auto& ph : c->pool) if (ph) svdb200_destroy(reinterpret_cast<svdb200_handle>(ph));
     c->pool.clear();
-    void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->red2, c->bar, c->prog,
+    void* ptrs[] = {c->a_dev, c->v, c->v2, c->vb, c->v2b, c->w, c->wpart, c->s, c->tau, c->red, c->red2, c->chol_ws, c->bar, c->prog,
                     c->d, c->e, c->sigma, c->qr_info, c->tileq, c->tilestate, c->tcsplit, c->bis_ws, c->batch_prog, c->batch_ws, c->de2};
     for (int k = 1; k < 2 * Ctx::kLanes; ++k) if (c->a_stage[k]) cudaFree(c->a_stage[k]);
     for (int l = 0; l < Ctx::kLanes; ++l) if (c->s1ctx[l]) svdb200_destroy(reinterpret_cast<svdb200_handle>(c->s1ctx[l]));
@@ -1026,9 +1039,29 @@ int svdb200_debug_stage2_timing(long long* out16) { return out16 ? stage2_debug_
 int svdb200_debug_stage2_fast_timing(long long* out16) { return out16 ? stage2_fast_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_blk_timing(long long* out16) { return out16 ? panel_blk_debug_read(out16) : SVDB200_E_ARG; }
+int svdb200_debug_panel_chol_timing(long long* out16) { return out16 ? panel_chol_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_set_panel_kernel(svdb200_handle h, int blocked) {
-    if (!h || blocked < 0 || blocked > 1) return SVDB200_E_ARG;
-    reinterpret_cast<Ctx*>(h)->panel_blk = blocked;
+    if (!h || blocked < 0 || blocked > 2) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    c->panel_blk = blocked >= 1;
+    c->panel_chol = blocked == 2;
+    for (auto* s : c->pool) if (s) { s->panel_blk = c->panel_blk; s->panel_chol = c->panel_chol; }
+    return 0;
+}
+int svdb200_set_chol_guard(svdb200_handle h, double guard) {
+    if (!h || !(guard >= 0.0)) return SVDB200_E_ARG;
+    reinterpret_cast<Ctx*>(h)->chol_guard = guard;
+    return 0;
+}
+int svdb200_chol_fallback_count(svdb200_handle h, long long* count) {
+    if (!h || !count) return SVDB200_E_ARG;
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    SVDB_CHECK(c, cudaSetDevice(c->device));
+    SVDB_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->aux_stream) SVDB_CHECK(c, cudaStreamSynchronize(c->aux_stream));
+    int st[2] = {0, 0};
+    SVDB_CHECK(c, cudaMemcpy(st, c->chol_ws, sizeof(st), cudaMemcpyDeviceToHost));
+    *count = st[1];
     return 0;
 }
 

@@ -77,6 +77,12 @@ struct Ctx {
     int onestage = 0;                       // stage-1 driver in the one-stage Golub-Kahan order (band 1, no skipped row reflector)
     int s2_ready = 0;                       // the pipeline's streams / counters / sub-handles below exist (all or nothing)
     int panel_blk = 1;                      // blocked panel kernel (one exchange per 8 columns, stage1_panel_blk.cu) where the shape allows
+    int panel_chol = 1;                     // Cholesky-QR panel with reconstructed Householder vectors (stage1_panel_chol.cu); env SVDB200_PANEL_CHOL=0: off
+    void* chol_ws = nullptr;                // its workspace: status word, [M1 | M2], partial Gram matrices (1 MB)
+    double chol_guard = 1e-3;               // smallest accepted pivot ratio R_jj^2 / G_jj; below, the exchange-based kernels redo the panel
+    const int* panel_run_if = nullptr;      // set while a gated fallback panel launch is being enqueued
+    int lookahead_reserve = 20;             // SMs the persistent tcgen05 rank update leaves free while a look-ahead panel runs beside it (SVDB200_RESERVE_SMS)
+    int reserve_now = 0;                    // set by the stage-1 drivers around the part of an update that overlaps a panel
     int overlap_safe = 0;                   // stage 1 may only use kernels without cross-cluster / grid-wide waits
     Ctx* s1ctx[kLanes] = {};                // sub-handles (own workspace + streams): stage 1 of two matrices at a time
     void* a_stage[2 * kLanes] = {};         // staging buffers + bidiagonal rows for the host-pointer variant
@@ -225,6 +231,7 @@ int probe_peak(Ctx* c, int kind, double* tflops);
 int probe_tc05_tf32(Ctx* c, double* tflops);
 int panel_reg_debug_read(long long* out16);
 int panel_blk_debug_read(long long* out16);
+int panel_chol_debug_read(long long* out16);
 int stage2_debug_read(long long* out16);
 int stage2_fast_debug_read(long long* out16);
 int tc05_selftest(Ctx* c, int a_mn, int b_mn, const float* a, const float* b, float* out, float* dump);

@@ -6,9 +6,16 @@
 //                  (all rows are local under a column distribution) and ncclBroadcast()s
 //                  [V | V S^T] (2*m*b elements); every rank updates its local trailing columns
 //                  with the same two GEMMs as the single-GPU path.
-//   LQ half-step : the b x n' row panel spans all ranks: ncclAllGather of the local pieces
-//                  (b*n' elements in total), every rank factorises the SAME assembled panel
-//                  redundantly (deterministic kernel => identical U on every rank, no broadcast),
+//   LQ half-step : the b x n' row panel spans all ranks.  Default: Cholesky-QR with reconstructed Householder vectors
+//                  (stage1_panel_chol.cu) -- every rank forms the Gram matrix of ITS columns of the row panel, ONE
+//                  ncclAllReduce of b^2-sized data in double ([G | top block]), the same b x b algebra on every rank,
+//                  then a local pass that leaves U^T and S U in the rank's own layout: a distributed (TSQR-like) panel
+//                  with 50 KB of traffic instead of a gather of b*n' elements and a redundant n'-wide factorisation.
+//                  The panel's status word is read back by the host (after the concurrent part of the QR update has been
+//                  enqueued): a row panel below the pivot-ratio guard -- e.g. the first one of a matrix with a large
+//                  common mean -- is redone through the fallback, identically on every rank.
+//                  Fallback (also: band not 8/16/32/64, panels narrower than 2 b, SVDB200_PANEL_CHOL=0): ncclAllGather of
+//                  the local pieces, every rank factorises the SAME assembled panel redundantly.
 //                  W = A U^T is a sum over the column distribution: local partial product +
 //                  ncclAllReduce(sum) of m' x b, then the local rank-b update.
 // Traffic per block step is O(n*b) elements against O(n^2*b/P) flops per rank.
@@ -20,6 +27,13 @@
 
 namespace svdb200 {
 template <typename T, bool kTrans> int launch_panel_public(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
+// distributed Cholesky-QR LQ panel (stage1_panel_chol.cu)
+size_t chol_dist_buf_elems(int b);
+bool chol_dist_supported(const Ctx* c, int b);
+template <typename T> int chol_dist_lq_gram(Ctx* c, const T* a2, size_t ldl, int b, int row0, int ncl, bool own_top, double* buf, cudaStream_t stream);
+template <typename T> int chol_dist_lq_finish(Ctx* c, T* a2, size_t ldl, int b, int row0, int ncl, bool own_top, const double* buf, T* ut_loc,
+                                              T* u2_loc, cudaStream_t stream);
+const int* chol_dist_status(Ctx* c);
 
 namespace {
 
@@ -71,6 +85,11 @@ struct Dist {
     void* bandsend = nullptr;    // ncl_max x (band+1) : this rank's band columns, packed
     void* bandall = nullptr;     // nranks x ncl_max x (band+1) : all-gather landing zone
     void* dense = nullptr;       // rank 0, svdvals only: n x n staging for stage 2 (allocated on first use)
+    double* lqbuf = nullptr;     // distributed LQ panel: [tile-packed Gram matrix | top block], all-reduced in double
+    int lq_dist = 1;             // 1: LQ panels by local Gram matrix + all-reduce (no gather of the row panel); 0: gather + redundant panel
+    int* h_status = nullptr;     // pinned: status words of the last distributed LQ panel (read back once per panel)
+    cudaEvent_t ev_status = nullptr;
+    long long lq_fallbacks = 0;  // row panels the Cholesky-QR path gave up on (redone through the gather path)
     size_t ncl_max = 0;
 };
 
@@ -241,7 +260,9 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
         const size_t np = n - o - band;                              // global width of the row panel
         const size_t mr = m - band;
         if (ahead) { SVDB_CHECK(c, cudaEventRecord(evR, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evR, 0)); }
-        {   // s1: gather the b x np row panel on every rank, factorise it redundantly, scatter the local slices
+        const bool own_top = (int)((k + 1) % P) == rk && ncl > 0;          // my first b trailing columns are the panel's top block
+        // s1: gather the b x np row panel on every rank, factorise it redundantly, scatter the local slices
+        auto lq_gather_path = [&]() -> int {
             size_t cnt = (size_t)b * d->ncl_max;
             pack_rows_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, s1>>>(A2, ldl, b, ncl, d->ncl_max, sendbuf);
             c->launches++;
@@ -258,10 +279,40 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
                                                                                         ut_loc, u2_loc);
                 c->launches++;
             }
+            return 0;
+        };
+        bool lq_pending = false;
+        if (d->lq_dist && chol_dist_supported(c, b) && np >= 2 * band) {
+            // s1: local Gram matrix -> all-reduce -> algebra (every rank) -> local second pass (gated on the guard); the
+            // status word comes back to the host, which looks at it only after the rest of the QR update is enqueued
+            const int row0 = own_top ? b : 0;
+            SVDB_TRY(chol_dist_lq_gram<T>(c, A2, ldl, b, row0, (int)ncl, own_top, d->lqbuf, s1));
+            if (P > 1) SVDB_NCCL(d, nccl().AllReduce(d->lqbuf, d->lqbuf, chol_dist_buf_elems(b), ncclFloat64, ncclSum, d->comm, s1));
+            SVDB_TRY(chol_dist_lq_finish<T>(c, A2, ldl, b, row0, (int)ncl, own_top, d->lqbuf, ut_loc, u2_loc, s1));
+            SVDB_CHECK(c, cudaMemcpyAsync(d->h_status, chol_dist_status(c), 4 * sizeof(int), cudaMemcpyDeviceToHost, s1));
+            SVDB_CHECK(c, cudaEventRecord(d->ev_status, s1));
+            lq_pending = true;
+        } else {
+            SVDB_TRY(lq_gather_path());
             if (ahead) SVDB_CHECK(c, cudaEventRecord(evL, s1));
         }
         // s0: the rest of the QR update runs beside the LQ panel
-        if (ncl > 0 && mr > 0) SVDB_TRY(rank_update<T>(c, A2 + band * ldl, ldl, mr, ncl, band, V2 + band * band, W, ncl));
+        if (ncl > 0 && mr > 0) {
+            c->reserve_now = ahead ? c->lookahead_reserve : 0;               // the LQ panel runs beside this
+            const int st = rank_update<T>(c, A2 + band * ldl, ldl, mr, ncl, band, V2 + band * band, W, ncl);
+            c->reserve_now = 0;
+            SVDB_TRY(st);
+        }
+        if (lq_pending) {
+            // Identical numbers on every rank => identical status => every rank takes the same branch (and issues the same
+            // collectives).  A row panel whose pivot ratio fell below the guard was left untouched: redo it by the gather path.
+            SVDB_CHECK(c, cudaEventSynchronize(d->ev_status));
+            if (d->h_status[0] != 0) {
+                d->lq_fallbacks++;
+                SVDB_TRY(lq_gather_path());
+            }
+            if (ahead) SVDB_CHECK(c, cudaEventRecord(evL, s1));
+        }
         if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, evL, 0));
         if (mr > 0) {
             T* A3 = a + (o + band) * ldl + lb0 * band;
@@ -278,8 +329,12 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
             }
             SVDB_TRY(qr_panel_and_bcast(k + 1));                           // s1: panel k+1 + broadcast
             if (ahead && ncl > 0) {
-                if (own_next) { if (ncl > band) SVDB_TRY(rank_update<T>(c, A3 + band, ldl, mr, ncl - band, band, W, u2_loc + band, ncl)); }
-                else SVDB_TRY(rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl));
+                c->reserve_now = c->lookahead_reserve;                       // QR panel k+1 (on its owner) runs beside this
+                int st = 0;
+                if (own_next) { if (ncl > band) st = rank_update<T>(c, A3 + band, ldl, mr, ncl - band, band, W, u2_loc + band, ncl); }
+                else st = rank_update<T>(c, A3, ldl, mr, ncl, band, W, u2_loc, ncl);
+                c->reserve_now = 0;
+                SVDB_TRY(st);
             }
         } else if (k + 1 < nb) {
             if (ahead) { SVDB_CHECK(c, cudaEventRecord(evP, s0)); SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0)); }
@@ -395,6 +450,9 @@ int svdb200_dist_create(svdb200_dist_handle* out, int device, int rank, int nran
     if (e == cudaSuccess) e = cudaMalloc(&d->vv, es * 2 * (n + 256) * band);
     if (e == cudaSuccess) e = cudaMalloc(&d->bandsend, es * d->ncl_max * (band + 1));
     if (e == cudaSuccess) e = cudaMalloc(&d->bandall, es * (size_t)nranks * d->ncl_max * (band + 1));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->lqbuf), sizeof(double) * (chol_dist_buf_elems((int)band) + 64));
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&d->h_status), 64, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_status, cudaEventDisableTiming);
     if (e != cudaSuccess) { int s2 = cuda_status(d->ctx, e, "cudaMalloc(dist)"); svdb200_dist_destroy(reinterpret_cast<svdb200_dist_handle>(d)); return s2; }
     if (nranks > 1) {
         ncclUniqueId id;
@@ -411,8 +469,10 @@ int svdb200_dist_destroy(svdb200_dist_handle h) {
     Dist* d = reinterpret_cast<Dist*>(h);
     if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
     if (d->comm) nccl().CommDestroy(d->comm);
-    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc, d->vv, d->bandsend, d->bandall, d->dense};
+    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc, d->vv, d->bandsend, d->bandall, d->dense, d->lqbuf};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (d->h_status) cudaFreeHost(d->h_status);
+    if (d->ev_status) cudaEventDestroy(d->ev_status);
     if (d->ctx) svdb200_destroy(reinterpret_cast<svdb200_handle>(d->ctx));
     delete d;
     return 0;
@@ -424,6 +484,7 @@ int svdb200_dist_set_stream(svdb200_dist_handle h, void* stream) {
 }
 
 long long svdb200_dist_launch_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->ctx->launches : -1; }
+long long svdb200_dist_lq_fallback_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->lq_fallbacks : -1; }
 
 int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle h, float* a, size_t n, size_t band) {
     if (!h || !a) return SVDB200_E_ARG;
@@ -458,6 +519,12 @@ int svdb200_dist_dense_to_band_dev_f64(svdb200_dist_handle h, double* a, size_t 
 SVDB_DIST_TYPED(float, f32, SVDB200_F32)
 SVDB_DIST_TYPED(double, f64, SVDB200_F64)
 #undef SVDB_DIST_TYPED
+
+int svdb200_dist_configure_panels(svdb200_dist_handle h, int lq_distributed) {
+    if (!h || lq_distributed < 0 || lq_distributed > 1) return SVDB200_E_ARG;
+    reinterpret_cast<Dist*>(h)->lq_dist = lq_distributed;
+    return 0;
+}
 
 int svdb200_dist_configure(svdb200_dist_handle h, int stage2_schedule, int qr_method, int tc05_mode) {
     if (!h) return SVDB200_E_ARG;

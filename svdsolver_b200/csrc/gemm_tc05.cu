@@ -748,10 +748,13 @@ int rank_update_tc05<float>(Ctx* c, float* cm, size_t ldc, int M, int N, int K, 
     SVDB_TRY(make_map(c, &tQl, ql, K, N, ldn, K, true));
     const int RB = (M + 127) / 128, NT = (N + 127) / 128;
     int chunk = 8;
-    while (chunk > 1 && (long long)RB * ((NT + chunk - 1) / chunk) < 2LL * c->num_sms) chunk >>= 1;
+    // persistent CTAs, one per SM -- minus the SMs left to a look-ahead panel on the high-priority stream (the panel's
+    // kernels need whole SMs: this kernel's CTAs never retire early)
+    const int sms = c->reserve_now > 0 && c->num_sms > 2 * c->reserve_now ? c->num_sms - c->reserve_now : c->num_sms;
+    while (chunk > 1 && (long long)RB * ((NT + chunk - 1) / chunk) < 2LL * sms) chunk >>= 1;
     const int NCH = (NT + chunk - 1) / chunk;
     int grid = RB * NCH;
-    if (grid > c->num_sms) grid = c->num_sms;
+    if (grid > sms) grid = sms;
     if (K == 64) {
         auto kern = rank_update_tc05_kernel<64>;
         SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::kSmem));

@@ -35,6 +35,11 @@ int launch_panel_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaSt
 // blocked kernel, one exchange per 8 columns (stage1_panel_blk.cu): same convention
 template <typename T, bool kTrans>
 int launch_panel_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
+// Cholesky-QR panel with reconstructed Householder vectors (stage1_panel_chol.cu): 0 = launched -- a fallback kernel gated
+// on chol_status() must follow in the stream --, 1 = shape not covered
+template <typename T, bool kTrans>
+int launch_panel_chol(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
+const int* chol_status(Ctx* c);
 
 namespace {
 
@@ -45,8 +50,10 @@ constexpr int kPanelThreads = 256;
 template <typename T, bool kTrans, bool kCluster>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_factor_kernel(T* __restrict__ A, size_t lda, int m, int b, int rows_per_cta, T* __restrict__ V, T* __restrict__ V2,
-                    T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar, int Gb, size_t sA, size_t sV) {
+                    T* __restrict__ S_out, T* __restrict__ red, unsigned* __restrict__ bar, int Gb, size_t sA, size_t sV,
+                    const int* __restrict__ run_if) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (run_if != nullptr && *run_if == 0) return;       // fallback launch behind the Cholesky-QR panel: only when it gave up
     const int tid = threadIdx.x, nt = blockDim.x;
     // Gb > 0: batched launch, clusters of Gb CTAs, one matrix (element strides sA / sV) per cluster
     const int G = Gb > 0 ? Gb : gridDim.x, g = Gb > 0 ? blockIdx.x % Gb : blockIdx.x;
@@ -246,11 +253,27 @@ inline size_t panel_smem_bytes(int rows, int b, size_t esz) {
 }
 
 template <typename T, bool kTrans>
+int launch_panel_exchange(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream);
+
+template <typename T, bool kTrans>
 int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 = nullptr, cudaStream_t stream = nullptr) {
     if (!stream) stream = c->stream;
     ProfScope ps(c, 0, 2.0 * (double)m * (double)b * (double)b);
     if (!V) V = reinterpret_cast<T*>(c->v);
     if (!V2) V2 = reinterpret_cast<T*>(c->v2);
+    c->panel_run_if = nullptr;
+    if (c->panel_chol) {
+        const int st = launch_panel_chol<T, kTrans>(c, a, lda, m, b, V, V2, stream);
+        if (st == 0) c->panel_run_if = chol_status(c);        // the exchange-based kernel below runs only if the guard tripped
+        else if (st != 1) return st;
+    }
+    const int st = launch_panel_exchange<T, kTrans>(c, a, lda, m, b, V, V2, stream);
+    c->panel_run_if = nullptr;
+    return st;
+}
+
+template <typename T, bool kTrans>
+int launch_panel_exchange(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream) {
     if (c->panel_blk) {
         int st = launch_panel_blk<T, kTrans>(c, a, lda, m, b, V, V2, stream);
         if (st != 1) return st;
@@ -288,14 +311,14 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, rows, V, V2, S, red, bar, 0, (size_t)0, (size_t)0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, rows, V, V2, S, red, bar, 0, (size_t)0, (size_t)0, c->panel_run_if);
             if (e == cudaSuccess) {
                 c->launches++;
                 return 0;
             }
             cudaGetLastError();           // cluster shape not schedulable here: use the grid transport
             c->cluster_ok = c->cluster_ok > 8 ? 8 : 0;
-            return launch_panel<T, kTrans>(c, a, lda, m, b, V, V2, stream);
+            return launch_panel_exchange<T, kTrans>(c, a, lda, m, b, V, V2, stream);
         }
     }
     // ---- cooperative-grid transport -----------------------------------------------------------------------
@@ -312,7 +335,8 @@ int launch_panel(Ctx* c, T* a, size_t lda, int m, int b, T* V = nullptr, T* V2 =
     SVDB_CHECK(c, cudaMemsetAsync(c->bar, 0, 2 * sizeof(unsigned), stream));
     int gb0 = 0;
     size_t zero = 0;
-    void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar, &gb0, &zero, &zero};
+    const int* run_if = c->panel_run_if;
+    void* args[] = {&a, &lda, &m, &b, &rows, &V, &V2, &S, &red, &bar, &gb0, &zero, &zero, &run_if};
     SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kPanelThreads), args, smem, stream));
     c->launches++;
     return 0;
@@ -363,7 +387,7 @@ int panel_batched(Ctx* c, T* a, size_t lda, size_t sA, int m, int b, T* V, T* V2
         T* az = a + (size_t)z0 * sA;
         T* vz = V + (size_t)z0 * sV;
         T* v2z = V2 + (size_t)z0 * sV;
-        SVDB_CHECK(c, cudaLaunchKernelEx(&cfg, kern, az, lda, m, b, rows, vz, v2z, S, red, bar, G, sA, sV));
+        SVDB_CHECK(c, cudaLaunchKernelEx(&cfg, kern, az, lda, m, b, rows, vz, v2z, S, red, bar, G, sA, sV, (const int*)nullptr));
         c->launches++;
     }
     return 0;
@@ -418,7 +442,12 @@ int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
                 }
                 SVDB_TRY((launch_panel<T, true>(c, A2, n, (int)nc, b, Vl, V2l, s1)));    // LQ panel (look-ahead)
                 if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[3], s1));
-                if (m > band) SVDB_TRY(rank_update<T>(c, A2 + band * n, n, m - band, nc, band, V2q + band * band, W, nc));
+                if (m > band) {
+                    c->reserve_now = ahead ? c->lookahead_reserve : 0;       // the LQ panel runs beside this
+                    const int st = rank_update<T>(c, A2 + band * n, n, m - band, nc, band, V2q + band * band, W, nc);
+                    c->reserve_now = 0;
+                    SVDB_TRY(st);
+                }
             } else {
                 SVDB_TRY(rank_update<T>(c, A2, n, m, nc, band, V2q, W, nc));             // A2 += (V S^T) W
             }
@@ -436,7 +465,12 @@ int stage1_panel_order(Ctx* c, T* a, size_t n, size_t band) {
                 }
                 SVDB_TRY((launch_panel<T, false>(c, A3, n, (int)mr, b, Vq, V2q, s1)));   // QR panel k+1 (look-ahead)
                 if (ahead) SVDB_CHECK(c, cudaEventRecord(c->lev[1], s1));
-                if (nc > band) SVDB_TRY(rank_update<T>(c, A3 + band, n, mr, nc - band, band, W, V2l + band, nc));
+                if (nc > band) {
+                    c->reserve_now = ahead ? c->lookahead_reserve : 0;       // QR panel k+1 runs beside this
+                    const int st = rank_update<T>(c, A3 + band, n, mr, nc - band, band, W, V2l + band, nc);
+                    c->reserve_now = 0;
+                    SVDB_TRY(st);
+                }
             }
         } else if (nc > 0) {
             // no LQ for this step (only when the trailing block is a single column): next QR panel directly,

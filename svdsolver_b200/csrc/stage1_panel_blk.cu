@@ -94,8 +94,9 @@ __host__ __device__ inline BlkSmem blk_smem(int rows, int b, size_t esz, const B
 template <typename T, bool kTrans, int CPL>
 __global__ void __launch_bounds__(kThreads, 1)
 panel_blk_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, char* __restrict__ gbuf, int NC,
-                 unsigned epoch, int ROWS, int dbl) {
+                 unsigned epoch, int ROWS, int dbl, const int* __restrict__ run_if) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (run_if != nullptr && *run_if == 0) return;       // fallback launch behind the Cholesky-QR panel: only when it gave up
     constexpr bool kFloat = sizeof(T) == 4;
     constexpr int C = kC;
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31, w = tid >> 5;
@@ -660,7 +661,7 @@ int launch_blk(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
         if (NC > max_clusters) return 1;
     }
     char* gbuf = reinterpret_cast<char*>(c->red2);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch, rows, dbl);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, gbuf, NC, ++c->panel_epoch, rows, dbl, c->panel_run_if);
     if (e != cudaSuccess) { cudaGetLastError(); return 1; }
     c->launches++;
     return 0;

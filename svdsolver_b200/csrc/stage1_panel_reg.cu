@@ -117,8 +117,9 @@ __host__ __device__ inline size_t stage_elems(int rows, int b, int max_cs) {
 template <typename T, bool kTrans, bool kCluster, int RPT, int CPL>
 __global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 && RPT * CPL <= 32) ? 2 : 1)
 panel_reg_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ V, T* __restrict__ V2, T* __restrict__ red,
-                 unsigned* __restrict__ bar, int NC, unsigned epoch) {
+                 unsigned* __restrict__ bar, int NC, unsigned epoch, const int* __restrict__ run_if) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (run_if != nullptr && *run_if == 0) return;       // fallback launch behind the Cholesky-QR panel: only when it gave up
     constexpr int ROWS = RPT * kWarps;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, w = tid >> 5;
     const int G = gridDim.x, g = blockIdx.x;
@@ -549,7 +550,7 @@ int launch_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
                 }
                 if (NC > max_clusters) continue;
             }
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, red, bar, NC, ++c->panel_epoch);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lda, m, b, V, V2, red, bar, NC, ++c->panel_epoch, c->panel_run_if);
             if (e == cudaSuccess) { c->launches++; return 0; }
             cudaGetLastError();
             if (NC == 1) {                     // cluster shape not schedulable here: smaller clusters, then the grid transport
@@ -564,13 +565,14 @@ int launch_reg(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t
     int nc0 = 0;
     if (cooperative) {
         unsigned ep0 = 0;
-        void* args[] = {&a, &lda, &m, &b, &V, &V2, &red, &bar, &nc0, &ep0};
+        const int* run_if = c->panel_run_if;
+        void* args[] = {&a, &lda, &m, &b, &V, &V2, &red, &bar, &nc0, &ep0, &run_if};
         SVDB_CHECK(c, cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(kThreads), args, smem, stream));
     } else {
         // look-ahead panels run beside the trailing update: a cooperative launch is gang-scheduled
         // and would wait for the update to drain; G <= #SMs CTAs of this size always become
         // co-resident once the update's CTAs retire, so the software barrier still completes.
-        kern<<<G, kThreads, smem, stream>>>(a, lda, m, b, V, V2, red, bar, nc0, 0u);
+        kern<<<G, kThreads, smem, stream>>>(a, lda, m, b, V, V2, red, bar, nc0, 0u, c->panel_run_if);
         SVDB_CHECK(c, cudaGetLastError());
     }
     c->launches++;

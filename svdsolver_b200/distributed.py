@@ -103,6 +103,12 @@ class DistHandle:
         if st != 0:
             raise capi.SvdB200Error(st, "svdb200_dist_configure")
 
+    def configure_panels(self, lq_distributed=1):
+        """1 (default): LQ panels by local Gram matrix + one all-reduce; 0: all-gather of the row panel, redundant factorisation"""
+        st = capi.lib().svdb200_dist_configure_panels(self.h, ctypes.c_int(lq_distributed))
+        if st != 0:
+            raise capi.SvdB200Error(st, "svdb200_dist_configure_panels")
+
     def launch_count(self):
         return int(capi.lib().svdb200_dist_launch_count(self.h))
 

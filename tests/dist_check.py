@@ -20,9 +20,12 @@ sys.path.insert(0, ROOT)
 from svdsolver_b200 import capi, distributed as D  # noqa: E402
 from svdsolver_b200.synth import uniform_matrix  # noqa: E402
 
+# (n, band, dtype, tolerance, lq_distributed): 1 = LQ panels through the local Gram matrix + one all-reduce (default),
+# 0 = all-gather of the row panel + redundant factorisation (the fallback path)
 CASES = {
-    "small": [(1024, 32, np.float64, 1e-10), (768, 64, np.float32, 1e-4), (512, 4, np.float64, 1e-10)],
-    "large": [(8192, 64, np.float32, 1e-4), (8192, 64, np.float64, 1e-10), (6144, 32, np.float32, 1e-4)],
+    "small": [(1024, 32, np.float64, 1e-10, 1), (768, 64, np.float32, 1e-4, 1), (512, 4, np.float64, 1e-10, 1), (1024, 32, np.float64, 1e-10, 0),
+              (768, 16, np.float32, 1e-4, 1)],
+    "large": [(8192, 64, np.float32, 1e-4, 1), (8192, 64, np.float64, 1e-10, 1), (6144, 32, np.float32, 1e-4, 1), (4096, 64, np.float32, 1e-4, 0)],
 }
 
 
@@ -44,7 +47,7 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
-    for n, band, dt, tol in CASES[which]:
+    for n, band, dt, tol, lqd in CASES[which]:
         tdt = torch.float32 if dt == np.float32 else torch.float64
         a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, dt)
         s = torch.cuda.Stream()
@@ -55,6 +58,7 @@ def main():
         with D.DistHandle(n, band, dt, rank, world, uid, device=lr) as h:
             h.set_stream(s.cuda_stream)
             h.configure(tc05_mode=2)
+            h.configure_panels(lqd)
             torch.cuda.synchronize()
             h.dense_to_band_dev(loc.data_ptr())
             h.gather_band_dev(loc.data_ptr(), packed.data_ptr())
@@ -67,6 +71,7 @@ def main():
         with D.DistHandle(n, band, dt, rank, world, uid2, device=lr) as h:
             h.set_stream(s.cuda_stream)
             h.configure(stage2_schedule=1, qr_method=2)
+            h.configure_panels(lqd)
             torch.cuda.synchronize()
             h.svdvals_dev(loc2.data_ptr(), sigma.data_ptr())
             s.synchronize()
@@ -90,7 +95,7 @@ def main():
             stol = 2e-5 if dt == np.float32 else 1e-11
             good = rel <= tol and below == 0.0 and band_ok and fro <= (1e-5 if dt == np.float32 else 1e-12) and serr <= stol
             ok &= good
-            print(f"dist n={n} band={band} {np.dtype(dt).name} ranks={world}: band rel diff vs 1-GPU {rel:.3e}, below-diag {below:.1e}, "
+            print(f"dist n={n} band={band} {np.dtype(dt).name} ranks={world} lq_dist={lqd}: band rel diff vs 1-GPU {rel:.3e}, below-diag {below:.1e}, "
                   f"gathered band == dense band: {band_ok}, |A|_F drift {fro:.2e}, dist_svdvals vs LAPACK {serr:.2e}  {'OK' if good else 'FAIL'}", flush=True)
         del loc, loc2
         torch.cuda.empty_cache()
