@@ -44,7 +44,9 @@ UNIT = "GFLOP/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one stage2_chase_kernel<double> launch at n = 3840, band 32 from the
 # committed ncu --set full capture (profiles/); None until measured
-S2_TRAFFIC = 4612608   # 3.450 MB read + 1.162 MB written (profiles/r01_summary.md, prof_r1_s2d: n = 3840, band 32, f64)
+S2_TRAFFIC = 4869888   # 3.519 MB read + 1.351 MB written (profiles/r02_ncu_stage2_fast.csv: stage2_fast_kernel<double>, n = 3840, band 32)
+S2_L2_BYTES = 14038780224   # lts__t_sectors.sum x 32 B of the same capture (algorithmic window bytes: 15.1e9)
+S2_NCU_MS = 50.70
 
 
 def flops(n):
@@ -421,7 +423,7 @@ def dist_stage1_config(args, capi, torch, dist, stream, dev, local_rank, rank, w
         out.update(one(world, rank, uid, 2))
         out["collectives"] = ("per block step: ncclBroadcast([V | V S^T]) of the QR panel, ncclAllReduce([Gram | top block], 50 KB, double) of the "
                               "distributed LQ panel, ncclAllReduce(W)") if world > 1 else "none (one rank)"
-        if world > 1:
+        if world > 1 and not os.environ.get("SKIP_N1"):
             t1 = torch.zeros(1, device=dev, dtype=torch.float64)
             if rank == 0:
                 import ctypes
@@ -611,8 +613,11 @@ def main():
             v = prof["stage2"]
             ach = v["work"] / (v["ms"] * 1e-3) * 1e-9
             peak = hbm_peak or 6650.0
-            roofline = {"bound": "hbm", "kernel": "stage2_chase_kernel<double> (band -> bidiagonal bulge chasing)",
+            roofline = {"bound": "hbm", "kernel": "stage2_fast_kernel<double> / stage2_chase_kernel<double> (band -> bidiagonal bulge chasing)",
                         "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": S2_TRAFFIC,
+                        "l2": {"achieved_gbs": round(S2_L2_BYTES / (S2_NCU_MS * 1e-3) * 1e-9, 1), "traffic": S2_L2_BYTES,
+                               "note": "L2 <-> SM bytes of the n = 3840 launch under ncu (lts__t_sectors.sum x 32 B) over its duration: every "
+                                       "window element goes through L2 once per op (the algorithmic figure), HBM sees only the compulsory band"},
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if hbm_peak else "fallback 6.65 TB/s",
                         "algorithmic_bytes": "4*b*n^2*sizeof(T) window bytes per launch (SURVEY 8d)",
                         "note": "dependency-latency bound by construction (4 window ops x n sweeps on the critical path, "

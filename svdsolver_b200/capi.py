@@ -247,6 +247,19 @@ class Handle:
         """one stage-1 panel (QR of the m x b column panel, or LQ of the b x m row panel when trans)"""
         self._check(self._fn("panel_factor_dev")(self.h, _p(a_ptr), Z(lda), Z(m), Z(b), ctypes.c_int(1 if trans else 0), _p(v_ptr), _p(v2_ptr)))
 
+    def set_panel_kernel(self, kind):
+        """stage-1 panel kernel: 2 = Cholesky-QR with reconstructed Householder vectors (default), 1 = blocked, 0 = per-column"""
+        self._check(lib().svdb200_set_panel_kernel(self.h, ctypes.c_int(kind)))
+
+    def set_chol_guard(self, guard):
+        """smallest pivot ratio the Cholesky-QR panel accepts before the exchange-based kernels redo the panel"""
+        self._check(lib().svdb200_set_chol_guard(self.h, ctypes.c_double(guard)))
+
+    def chol_fallback_count(self):
+        v = ctypes.c_longlong(0)
+        self._check(lib().svdb200_chol_fallback_count(self.h, ctypes.byref(v)))
+        return int(v.value)
+
     def last_timings(self):
         v = [ctypes.c_double(0) for _ in range(5)]
         self._check(lib().svdb200_last_timings(self.h, *[ctypes.byref(x) for x in v]))

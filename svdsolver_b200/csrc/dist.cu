@@ -34,6 +34,12 @@ template <typename T> int chol_dist_lq_gram(Ctx* c, const T* a2, size_t ldl, int
 template <typename T> int chol_dist_lq_finish(Ctx* c, T* a2, size_t ldl, int b, int row0, int ncl, bool own_top, const double* buf, T* ut_loc,
                                               T* u2_loc, cudaStream_t stream);
 const int* chol_dist_status(Ctx* c);
+// distributed Cholesky-QR QR panel: owner part (pass 1, algebra, pack), then the second pass on every rank
+size_t chol_dist_qr_elems(size_t m, int b);
+const int* chol_dist_qr_status(Ctx* c);
+template <typename T> int chol_dist_qr_owner(Ctx* c, T* a, size_t lda, int m, int b, T* qsend, cudaStream_t stream);
+template <typename T> int chol_dist_qr_all(Ctx* c, T* qsend, int m, int b, T* V, T* V2, cudaStream_t stream);
+template <typename T> int chol_dist_qr_owner_early(Ctx* c, T* a, size_t lda, int m, int b, T* qsend, int phase, cudaStream_t stream);
 
 namespace {
 
@@ -87,8 +93,14 @@ struct Dist {
     void* dense = nullptr;       // rank 0, svdvals only: n x n staging for stage 2 (allocated on first use)
     double* lqbuf = nullptr;     // distributed LQ panel: [tile-packed Gram matrix | top block], all-reduced in double
     int lq_dist = 1;             // 1: LQ panels by local Gram matrix + all-reduce (no gather of the row panel); 0: gather + redundant panel
-    int* h_status = nullptr;     // pinned: status words of the last distributed LQ panel (read back once per panel)
-    cudaEvent_t ev_status = nullptr;
+    int* h_status = nullptr;     // pinned: [0..3] status words of the last distributed LQ panel, [8..11] of the last QR panel
+    cudaEvent_t ev_status = nullptr, ev_qstatus = nullptr;
+    void* qsend = nullptr;       // QR panel message: raw rows | [M1 | M2] | top blocks of V, V2 | status
+    int qr_dist = 1;             // 1: QR panels travel as raw rows + band x band factors (second pass on every rank); 0: [V | V S^T]
+    int qr_early = 1;            // the raw rows are broadcast on a third stream while the owner factorises (SVDB200_DIST_EARLY_BCAST=0: off)
+    cudaStream_t bc_stream = nullptr;
+    cudaEvent_t ev_raw = nullptr, ev_rawdone = nullptr;
+    long long qr_fallbacks = 0;
     long long lq_fallbacks = 0;  // row panels the Cholesky-QR path gave up on (redone through the gather path)
     size_t ncl_max = 0;
 };
@@ -223,13 +235,71 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
         SVDB_CHECK(c, cudaEventRecord(evP, s0));
         SVDB_CHECK(c, cudaStreamWaitEvent(s1, evP, 0));
     }
-    // QR panel 0 + broadcast
-    auto qr_panel_and_bcast = [&](size_t k) -> int {
+    // QR panel k: factorisation on its owner + broadcast of the reflectors.  Fast path (Cholesky-QR panel): the owner runs
+    // pass 1 and the b x b algebra and broadcasts the RAW panel rows with the small factors; every rank then forms
+    // [V | V S^T] with the second pass on its copy -- half the bytes of broadcasting [V | V S^T], and the copy arrives in the
+    // layout the update reads.  The panel's status word travels with the message and is read by the host in qr_panel_finish
+    // (top of the step that needs V): a panel below the pivot-ratio guard is redone by the exchange-based kernels on the owner
+    // and broadcast as [V | V S^T], identically decided on every rank.
+    bool qr_pending = false;
+    size_t qr_pending_k = 0;
+    auto qr_panel_slow = [&](size_t k, bool allow_chol) -> int {
         const size_t o = k * band, m = n - o;
         const int owner = (int)(k % P);
         T* v2k = V + m * band;
-        if (rk == owner) SVDB_TRY((launch_panel_public<T, false>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, V, v2k, s1)));
+        if (rk == owner) {
+            const int keep = c->panel_chol;
+            if (!allow_chol) c->panel_chol = 0;
+            const int st = launch_panel_public<T, false>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, V, v2k, s1);
+            c->panel_chol = keep;
+            SVDB_TRY(st);
+        }
         if (P > 1) SVDB_NCCL(d, nccl().Broadcast(V, V, 2 * m * band, nccl_type<T>(), owner, d->comm, s1));
+        return 0;
+    };
+    auto qr_panel_and_bcast = [&](size_t k) -> int {
+        const size_t o = k * band, m = n - o;
+        const int owner = (int)(k % P);
+        qr_pending = false;
+        if (P > 1 && d->qr_dist && chol_dist_supported(c, b) && m >= 2 * band) {
+            T* qs = reinterpret_cast<T*>(d->qsend);
+            if (ahead && d->qr_early && d->bc_stream) {
+                // the raw rows travel on a third stream while the owner runs pass 1 and the algebra on its copy; the small
+                // tail of the message ([M1 | M2], top blocks, status) follows on s1.  Every rank issues the two broadcasts
+                // in this order.
+                cudaStream_t s2 = d->bc_stream;
+                const size_t nraw = (m - band) * band, ntail = 4 * band * band + 4;
+                if (rk == owner) SVDB_TRY(chol_dist_qr_owner_early<T>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, qs, 0, s1));
+                SVDB_CHECK(c, cudaEventRecord(d->ev_raw, s1));                 // (non-owners: the previous panel's copy has been consumed)
+                SVDB_CHECK(c, cudaStreamWaitEvent(s2, d->ev_raw, 0));
+                SVDB_NCCL(d, nccl().Broadcast(qs, qs, nraw, nccl_type<T>(), owner, d->comm, s2));
+                SVDB_CHECK(c, cudaEventRecord(d->ev_rawdone, s2));
+                if (rk == owner) SVDB_TRY(chol_dist_qr_owner_early<T>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, qs, 1, s1));
+                SVDB_NCCL(d, nccl().Broadcast(qs + nraw, qs + nraw, ntail, nccl_type<T>(), owner, d->comm, s1));
+                SVDB_CHECK(c, cudaStreamWaitEvent(s1, d->ev_rawdone, 0));
+            } else {
+                if (rk == owner) SVDB_TRY(chol_dist_qr_owner<T>(c, a + o * ldl + (k / P) * band, ldl, (int)m, b, qs, s1));
+                SVDB_NCCL(d, nccl().Broadcast(qs, qs, chol_dist_qr_elems(m, b), nccl_type<T>(), owner, d->comm, s1));
+            }
+            SVDB_TRY(chol_dist_qr_all<T>(c, qs, (int)m, b, V, V + m * band, s1));
+            SVDB_CHECK(c, cudaMemcpyAsync(d->h_status + 8, chol_dist_qr_status(c), 4 * sizeof(int), cudaMemcpyDeviceToHost, s1));
+            SVDB_CHECK(c, cudaEventRecord(d->ev_qstatus, s1));
+            qr_pending = true;
+            qr_pending_k = k;
+            return 0;
+        }
+        SVDB_TRY(qr_panel_slow(k, true));
+        if (ahead) SVDB_CHECK(c, cudaEventRecord(evQ, s1));
+        return 0;
+    };
+    auto qr_panel_finish = [&]() -> int {
+        if (!qr_pending) return 0;
+        qr_pending = false;
+        SVDB_CHECK(c, cudaEventSynchronize(d->ev_qstatus));
+        if (d->h_status[8] != 0) {
+            d->qr_fallbacks++;
+            SVDB_TRY(qr_panel_slow(qr_pending_k, false));
+        }
         if (ahead) SVDB_CHECK(c, cudaEventRecord(evQ, s1));
         return 0;
     };
@@ -241,6 +311,7 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
         const size_t ncl = ldl - lb0 * band;                         // local trailing columns
         V2 = V + m * band;
         // ---- QR half-step ------------------------------------------------------------------------------
+        SVDB_TRY(qr_panel_finish());                                 // (host: status of panel k; fallback if it was given up)
         if (ahead) SVDB_CHECK(c, cudaStreamWaitEvent(s0, evQ, 0));   // reflectors of panel k have arrived
         T* A2 = a + o * ldl + lb0 * band;
         if (ncl > 0) {
@@ -341,6 +412,7 @@ int dist_stage1(Dist* d, T* a, size_t n, size_t band) {
             SVDB_TRY(qr_panel_and_bcast(k + 1));
         }
     }
+    SVDB_TRY(qr_panel_finish());
     if (ahead) {   // everything the aux stream did is ordered before the caller's next work on the main stream
         SVDB_CHECK(c, cudaEventRecord(evQ, s1));
         SVDB_CHECK(c, cudaStreamWaitEvent(s0, evQ, 0));
@@ -453,6 +525,17 @@ int svdb200_dist_create(svdb200_dist_handle* out, int device, int rank, int nran
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->lqbuf), sizeof(double) * (chol_dist_buf_elems((int)band) + 64));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&d->h_status), 64, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_status, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_qstatus, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_raw, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_rawdone, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&d->bc_stream, cudaStreamNonBlocking, hi);
+        const char* eb = getenv("SVDB200_DIST_EARLY_BCAST");
+        if (eb && eb[0] == '0') d->qr_early = 0;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&d->qsend, es * ((n + 256) * band + 4 * band * band + 64));
     if (e != cudaSuccess) { int s2 = cuda_status(d->ctx, e, "cudaMalloc(dist)"); svdb200_dist_destroy(reinterpret_cast<svdb200_dist_handle>(d)); return s2; }
     if (nranks > 1) {
         ncclUniqueId id;
@@ -469,10 +552,14 @@ int svdb200_dist_destroy(svdb200_dist_handle h) {
     Dist* d = reinterpret_cast<Dist*>(h);
     if (d->ctx) { cudaSetDevice(d->ctx->device); cudaStreamSynchronize(d->ctx->stream); }
     if (d->comm) nccl().CommDestroy(d->comm);
-    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc, d->vv, d->bandsend, d->bandall, d->dense, d->lqbuf};
+    void* ptrs[] = {d->rowpanel, d->gather, d->sendbuf, d->ut_loc, d->u2_loc, d->vv, d->bandsend, d->bandall, d->dense, d->lqbuf, d->qsend};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (d->h_status) cudaFreeHost(d->h_status);
     if (d->ev_status) cudaEventDestroy(d->ev_status);
+    if (d->ev_qstatus) cudaEventDestroy(d->ev_qstatus);
+    if (d->ev_raw) cudaEventDestroy(d->ev_raw);
+    if (d->ev_rawdone) cudaEventDestroy(d->ev_rawdone);
+    if (d->bc_stream) { cudaStreamSynchronize(d->bc_stream); cudaStreamDestroy(d->bc_stream); }
     if (d->ctx) svdb200_destroy(reinterpret_cast<svdb200_handle>(d->ctx));
     delete d;
     return 0;
@@ -484,7 +571,7 @@ int svdb200_dist_set_stream(svdb200_dist_handle h, void* stream) {
 }
 
 long long svdb200_dist_launch_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->ctx->launches : -1; }
-long long svdb200_dist_lq_fallback_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->lq_fallbacks : -1; }
+long long svdb200_dist_lq_fallback_count(svdb200_dist_handle h) { return h ? reinterpret_cast<Dist*>(h)->lq_fallbacks + reinterpret_cast<Dist*>(h)->qr_fallbacks : -1; }
 
 int svdb200_dist_dense_to_band_dev_f32(svdb200_dist_handle h, float* a, size_t n, size_t band) {
     if (!h || !a) return SVDB200_E_ARG;
@@ -523,6 +610,7 @@ SVDB_DIST_TYPED(double, f64, SVDB200_F64)
 int svdb200_dist_configure_panels(svdb200_dist_handle h, int lq_distributed) {
     if (!h || lq_distributed < 0 || lq_distributed > 1) return SVDB200_E_ARG;
     reinterpret_cast<Dist*>(h)->lq_dist = lq_distributed;
+    reinterpret_cast<Dist*>(h)->qr_dist = lq_distributed;
     return 0;
 }
 

@@ -819,6 +819,169 @@ template int chol_dist_lq_gram<float>(Ctx*, const float*, size_t, int, int, int,
 template int chol_dist_lq_gram<double>(Ctx*, const double*, size_t, int, int, int, bool, double*, cudaStream_t);
 template int chol_dist_lq_finish<float>(Ctx*, float*, size_t, int, int, int, bool, const double*, float*, float*, cudaStream_t);
 template int chol_dist_lq_finish<double>(Ctx*, double*, size_t, int, int, int, bool, const double*, double*, double*, cudaStream_t);
+// ---- distributed QR panel (dist.cu): the m x b column panel lives on one rank ------------------------------------------------
+// The owner runs pass 1 and the algebra, then ONE broadcast carries the raw rows b .. m-1 of the panel plus [M1 | M2], the
+// top blocks of V and V2 and the status ((m - b) b + 4 b^2 + 4 elements instead of the 2 m b of [V | V S^T]); every rank runs
+// the second pass on its copy.
+namespace {
+template <typename T>
+__global__ void qr_pack_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ raw, T* __restrict__ flag, const int* __restrict__ status) {
+    const bool bad = status[0] != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flag[0] = bad ? (T)1 : (T)0;
+    if (bad) return;
+    const size_t tot = (size_t)(m - b) * b;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / b, cc = e - r * b;
+        T* src = A + (r + b) * lda + cc;
+        raw[e] = *src;
+        *src = (T)0;
+    }
+}
+// early variant: the raw rows leave before the factorisation (the broadcast overlaps pass 1 and the algebra, which then read the
+// contiguous copy); the panel rows are zeroed afterwards, once the status is known
+template <typename T>
+__global__ void qr_copy_kernel(const T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ raw) {
+    const size_t tot = (size_t)(m - b) * b;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / b, cc = e - r * b;
+        raw[e] = A[(r + b) * lda + cc];
+    }
+}
+template <typename T>
+__global__ void qr_zero_kernel(T* __restrict__ A, size_t lda, int m, int b, T* __restrict__ flag, const int* __restrict__ status) {
+    const bool bad = status[0] != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flag[0] = bad ? (T)1 : (T)0;
+    if (bad) return;
+    const size_t tot = (size_t)(m - b) * b;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / b, cc = e - r * b;
+        A[(r + b) * lda + cc] = (T)0;
+    }
+}
+template <typename T>
+__global__ void qr_unpack_kernel(const T* __restrict__ small, int b, T* __restrict__ V, T* __restrict__ V2, int* __restrict__ status) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = small[2 * b * b] != (T)0;
+    if (e == 0) status[0] = bad ? 1 : 0;
+    if (bad || e >= b * b) return;
+    V[e] = small[e];
+    V2[e] = small[b * b + e];
+}
+
+template <typename T, int B>
+int dist_qr_owner(Ctx* c, T* a, size_t lda, int m, T* qsend, cudaStream_t stream) {
+    char* ws = reinterpret_cast<char*>(c->chol_ws);
+    int* status = reinterpret_cast<int*>(ws) + 8;
+    double* part = reinterpret_cast<double*>(ws + 256 + 64 * 128 * 8);
+    T* raw = qsend;
+    T* mcat = qsend + (size_t)(m - B) * B;
+    T* vtop = mcat + 2 * B * B;
+    T* v2top = vtop + B * B;
+    T* flag = v2top + B * B;
+    const GramShape g = gram_shape(m - B, c->num_sms);
+    SVDB_TRY((gram_launch<T, false, B>(c, a, lda, B, m, part, g, stream)));
+    auto kern = chol_algebra_kernel<T, false, B>;
+    const size_t smem = chol_algebra_smem(B);
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
+    c->launches++;
+    const size_t tot = (size_t)(m - B) * B;
+    int blocks = (int)std::min<size_t>((tot + 1023) / 1024, (size_t)4 * c->num_sms);
+    qr_pack_kernel<T><<<blocks, 256, 0, stream>>>(a, lda, m, B, raw, flag, status);
+    c->launches++;
+    SVDB_CHECK(c, cudaGetLastError());
+    return 0;
+}
+// early variant, owner: phase 0 = copy the raw rows out (then the caller starts their broadcast); phase 1 = pass 1 on the copy,
+// algebra, flag, zeros into the panel rows (then the caller broadcasts the small tail of the message)
+template <typename T, int B>
+int dist_qr_owner_early(Ctx* c, T* a, size_t lda, int m, T* qsend, int phase, cudaStream_t stream) {
+    char* ws = reinterpret_cast<char*>(c->chol_ws);
+    int* status = reinterpret_cast<int*>(ws) + 8;
+    double* part = reinterpret_cast<double*>(ws + 256 + 64 * 128 * 8);
+    T* raw = qsend;
+    T* mcat = qsend + (size_t)(m - B) * B;
+    T* vtop = mcat + 2 * B * B;
+    T* v2top = vtop + B * B;
+    T* flag = v2top + B * B;
+    const size_t tot = (size_t)(m - B) * B;
+    const int blocks = (int)std::min<size_t>((tot + 1023) / 1024, (size_t)4 * c->num_sms);
+    if (phase == 0) {
+        qr_copy_kernel<T><<<blocks, 256, 0, stream>>>(a, lda, m, B, raw);
+        c->launches++;
+        SVDB_CHECK(c, cudaGetLastError());
+        return 0;
+    }
+    const GramShape g = gram_shape(m - B, c->num_sms);
+    SVDB_TRY((gram_launch<T, false, B>(c, raw, (size_t)B, 0, m - B, part, g, stream)));
+    auto kern = chol_algebra_kernel<T, false, B>;
+    const size_t smem = chol_algebra_smem(B);
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
+    c->launches++;
+    qr_zero_kernel<T><<<blocks, 256, 0, stream>>>(a, lda, m, B, flag, status);
+    c->launches++;
+    SVDB_CHECK(c, cudaGetLastError());
+    return 0;
+}
+template <typename T, int B>
+int dist_qr_all(Ctx* c, T* qsend, int m, T* V, T* V2, cudaStream_t stream) {
+    char* ws = reinterpret_cast<char*>(c->chol_ws);
+    int* status = reinterpret_cast<int*>(ws) + 8;
+    T* raw = qsend;
+    T* mcat = qsend + (size_t)(m - B) * B;
+    qr_unpack_kernel<T><<<(B * B + 255) / 256, 256, 0, stream>>>(mcat + 2 * B * B, B, V, V2, status);
+    c->launches++;
+    auto kern = chol_apply_kernel<T, false, B>;
+    const size_t smem = chol_apply_smem(B, sizeof(T));
+    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (m - B + kApplyRows - 1) / kApplyRows;
+    kern<<<grid, kApplyThreads, smem, stream>>>(raw, (size_t)B, 0, m - B, mcat, V + (size_t)B * B, V2 + (size_t)B * B, (size_t)B, (size_t)1, status);
+    c->launches++;
+    SVDB_CHECK(c, cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+size_t chol_dist_qr_elems(size_t m, int b) { return (m - b) * b + 4 * (size_t)b * b + 4; }
+const int* chol_dist_qr_status(Ctx* c) { return reinterpret_cast<const int*>(c->chol_ws) + 8; }
+template <typename T>
+int chol_dist_qr_owner(Ctx* c, T* a, size_t lda, int m, int b, T* qsend, cudaStream_t stream) {
+    switch (b) {
+        case 8: return dist_qr_owner<T, 8>(c, a, lda, m, qsend, stream);
+        case 16: return dist_qr_owner<T, 16>(c, a, lda, m, qsend, stream);
+        case 32: return dist_qr_owner<T, 32>(c, a, lda, m, qsend, stream);
+        case 64: return dist_qr_owner<T, 64>(c, a, lda, m, qsend, stream);
+        default: return SVDB200_E_CAPACITY;
+    }
+}
+template <typename T>
+int chol_dist_qr_owner_early(Ctx* c, T* a, size_t lda, int m, int b, T* qsend, int phase, cudaStream_t stream) {
+    switch (b) {
+        case 8: return dist_qr_owner_early<T, 8>(c, a, lda, m, qsend, phase, stream);
+        case 16: return dist_qr_owner_early<T, 16>(c, a, lda, m, qsend, phase, stream);
+        case 32: return dist_qr_owner_early<T, 32>(c, a, lda, m, qsend, phase, stream);
+        case 64: return dist_qr_owner_early<T, 64>(c, a, lda, m, qsend, phase, stream);
+        default: return SVDB200_E_CAPACITY;
+    }
+}
+template int chol_dist_qr_owner_early<float>(Ctx*, float*, size_t, int, int, float*, int, cudaStream_t);
+template int chol_dist_qr_owner_early<double>(Ctx*, double*, size_t, int, int, double*, int, cudaStream_t);
+template <typename T>
+int chol_dist_qr_all(Ctx* c, T* qsend, int m, int b, T* V, T* V2, cudaStream_t stream) {
+    switch (b) {
+        case 8: return dist_qr_all<T, 8>(c, qsend, m, V, V2, stream);
+        case 16: return dist_qr_all<T, 16>(c, qsend, m, V, V2, stream);
+        case 32: return dist_qr_all<T, 32>(c, qsend, m, V, V2, stream);
+        case 64: return dist_qr_all<T, 64>(c, qsend, m, V, V2, stream);
+        default: return SVDB200_E_CAPACITY;
+    }
+}
+template int chol_dist_qr_owner<float>(Ctx*, float*, size_t, int, int, float*, cudaStream_t);
+template int chol_dist_qr_owner<double>(Ctx*, double*, size_t, int, int, double*, cudaStream_t);
+template int chol_dist_qr_all<float>(Ctx*, float*, int, int, float*, float*, cudaStream_t);
+template int chol_dist_qr_all<double>(Ctx*, double*, int, int, double*, double*, cudaStream_t);
+
 // panels the distributed LQ path gave up on since the handle was created (device word; the caller synchronises)
 const int* chol_dist_status(Ctx* c) { return reinterpret_cast<const int*>(c->chol_ws) + 4; }
 

@@ -92,11 +92,12 @@ def test_many_pipeline_stage2_bit_exact_at_bench_sizes(capi, oracle, suf):
 
 
 # ------------------------------------------------------------------ panel order vs oracle at a larger size ----
-@pytest.mark.parametrize("blocked", [1, 0])
+@pytest.mark.parametrize("blocked", [2, 1, 0])
 @pytest.mark.parametrize("n,b,suf", [(640, 32, "f64"), (640, 32, "f32"), (768, 64, "f64"), (768, 64, "f32"), (512, 8, "f32"), (512, 8, "f64"),
                                      (1024, 32, "f64"), (512, 16, "f32")])
 def test_stage1_panel_order_vs_oracle_larger(capi, oracle, n, b, suf, blocked):
-    """Signed parity with the oracle's panel order for both panel kernels (blocked: one exchange per 8 columns; per-column).
+    """Signed parity with the oracle's panel order for the three panel kernels (2: Cholesky-QR with reconstructed Householder
+    vectors, the default; 1: blocked, one exchange per 8 columns; 0: per-column).
     Double: every sign must agree.  Float: a pivot that is tiny relative to fp32 round-off may legitimately come out with the
     other sign (the rule s = -sign(x0) is discontinuous; 1e-5 relative noise against ~10^3 pivots of size O(1)), which
     re-signs rows / columns of the band; such flips are accepted only as an exact D1 B D2 scaling, at the same tolerance."""
@@ -266,3 +267,92 @@ def test_batch_pool_many_tall_matrices(capi):
     s = sg.cpu().numpy()
     assert np.all(np.isfinite(s)) and np.all(np.diff(s, axis=1) <= 0)
     assert np.abs(s[5] - one.cpu().numpy()).max() <= 1e-11 * s[5, 0]
+
+
+# ------------------------------------------------------------------ Cholesky-QR panel (stage1_panel_chol.cu) ----
+def _panel_case(capi, torch, h, a0, m, b, trans, kind):
+    import ctypes
+    h.set_panel_kernel(kind)
+    a = a0.clone()
+    v = torch.empty(m, b, device="cuda", dtype=a0.dtype)
+    v2 = torch.empty(m * b, device="cuda", dtype=a0.dtype)
+    h.panel_factor_dev(a.data_ptr(), a.shape[1], m, b, trans, v.data_ptr(), v2.data_ptr())
+    h.synchronize()
+    R = (a.T if trans else a).double()
+    V = v.double()
+    V2 = (v2.view(b, m).T if trans else v2.view(m, b)).double()
+    return R, V, V2
+
+
+@pytest.mark.parametrize("suf,b,m", [("f64", 32, 64), ("f64", 32, 3000), ("f32", 32, 1920), ("f64", 64, 128), ("f64", 64, 4100), ("f32", 64, 16384),
+                                     ("f64", 16, 520), ("f32", 8, 1000)])
+@pytest.mark.parametrize("trans", [0, 1])
+def test_chol_panel_equals_per_column_panel(capi, suf, b, m, trans):
+    """One stage-1 panel (qr / lq of svd_parallel.h:133-226, sign rule of svd_serial.h:194-201): the Cholesky-QR kernel must give
+    the per-column kernel's R, V and V S^T (the Householder factorisation is unique once the sign rule is fixed), must not
+    fall back on a well-conditioned panel, and its compact-WY factors must reproduce Q^T A = [R; 0]."""
+    import torch
+    tdt = torch.float32 if suf == "f32" else torch.float64
+    tol = 2e-6 if suf == "f32" else 2e-13
+    g = torch.Generator(device="cuda").manual_seed(1000 * b + m)
+    a0 = torch.rand((b, m) if trans else (m, b), device="cuda", dtype=tdt, generator=g) * 5
+    with capi.Handle(m, b, DT[suf]) as h:
+        R2, V, V2 = _panel_case(capi, torch, h, a0, m, b, trans, 2)
+        assert h.chol_fallback_count() == 0
+        R0, V0, V20 = _panel_case(capi, torch, h, a0, m, b, trans, 0)
+    scale = float(R0.abs().max())
+    assert float((R2[:b] - R0[:b]).abs().max()) <= tol * scale
+    assert float(R2[b:].abs().max()) == 0.0 and float(R2[:b].tril(-1).abs().max()) == 0.0       # exact zeros below the diagonal
+    assert float((V - V0).abs().max()) <= 50 * tol
+    assert float((V2 - V20).abs().max()) <= 50 * tol
+    X = (a0.T if trans else a0).double()
+    QtX = X + V2 @ (V.T @ X)
+    assert float((QtX[:b] - R2[:b]).abs().max()) <= 100 * tol * float(X.abs().max())
+    assert float(QtX[b:].abs().max()) <= 100 * tol * float(X.abs().max())
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_chol_panel_guard_falls_back_inside_the_call(capi, suf):
+    """Panels below the pivot-ratio guard are redone by the exchange-based kernel enqueued behind the Cholesky-QR kernels (gated
+    on the status word): (a) with the guard forced to 0.99 every panel falls back and the result equals the blocked kernel's
+    bit for bit; (b) a panel with a repeated column (singular Gram matrix) falls back with the default guard and still gives
+    an orthogonal factorisation with R = Q^T A."""
+    import torch
+    tdt = torch.float32 if suf == "f32" else torch.float64
+    m, b = 2048, 32
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a0 = torch.rand(m, b, device="cuda", dtype=tdt, generator=g) * 5
+    with capi.Handle(m, b, DT[suf]) as h:
+        h.set_chol_guard(0.99)
+        Rg, Vg, V2g = _panel_case(capi, torch, h, a0, m, b, 0, 2)
+        assert h.chol_fallback_count() == 1
+        R1, V1, V21 = _panel_case(capi, torch, h, a0, m, b, 0, 1)
+        assert torch.equal(Rg, R1) and torch.equal(Vg, V1) and torch.equal(V2g, V21)
+        h.set_chol_guard(1e-3)
+        a1 = a0.clone()
+        a1[:, 5] = a1[:, 2]                                   # exactly dependent columns
+        R, V, V2 = _panel_case(capi, torch, h, a1, m, b, 0, 2)
+        assert h.chol_fallback_count() == 2
+        X = a1.double()
+        QtX = X + V2 @ (V.T @ X)
+        tol = 1e-4 if suf == "f32" else 1e-11
+        assert float((QtX[:b] - R[:b]).abs().max()) <= tol * float(X.abs().max())
+        assert float(QtX[b:].abs().max()) <= tol * float(X.abs().max())
+
+
+@pytest.mark.parametrize("suf,n,b", [("f64", 2048, 32), ("f32", 2048, 64)])
+def test_stage1_chol_panels_vs_blocked_panels(capi, suf, n, b):
+    """Whole stage 1 with the Cholesky-QR panels against the same driver with the blocked panels (same factorisation)."""
+    a = uniform_matrix(n, n, 586 + n, 0.0, 5.0, DT[suf])
+    with capi.Handle(n, b, DT[suf]) as h:
+        h.set_panel_kernel(2)
+        out2 = h.dense_to_band(a, b, capi.ORDER_PANEL)
+        fb = h.chol_fallback_count()
+        h.set_panel_kernel(1)
+        out1 = h.dense_to_band(a, b, capi.ORDER_PANEL)
+    assert fb <= 4                                            # (the first row panel of a U[0,5) matrix is close to the guard)
+    assert np.abs(np.tril(out2, -1)).max() == 0
+    rel = band_rel(out2, out1, b)
+    if rel > TOL[suf] and suf == "f32":
+        rel, _ = band_rel_mod_signs(out2, out1, b)
+    assert rel <= TOL[suf]
