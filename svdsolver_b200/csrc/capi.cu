@@ -193,6 +193,7 @@ static void inherit_settings(const Ctx* c, Ctx* s) {
     s->lookahead = c->lookahead; s->panel_reg = c->panel_reg; s->panel_reg_min = c->panel_reg_min;
     s->panel_blk = c->panel_blk;
     s->panel_chol = c->panel_chol;
+    s->pipe_chol = c->pipe_chol;
     s->lookahead_reserve = c->lookahead_reserve;
     s->chol_guard = c->chol_guard;
 }
@@ -732,6 +733,8 @@ int svdb200_create(svdb200_handle* out, int device, size_t max_n, size_t band, i
         if (rs && rs[0]) c->lookahead_reserve = atoi(rs);
         const char* pc = getenv("SVDB200_PANEL_CHOL");
         if (pc && pc[0] == '0') c->panel_chol = 0;
+        const char* pp = getenv("SVDB200_PIPE_CHOL");
+        if (pp && pp[0]) c->pipe_chol = pp[0] != '0';
         const char* pg = getenv("SVDB200_CHOL_GUARD");
         if (pg && pg[0]) c->chol_guard = atof(pg);
     }

@@ -78,6 +78,7 @@ struct Ctx {
     int s2_ready = 0;                       // the pipeline's streams / counters / sub-handles below exist (all or nothing)
     int panel_blk = 1;                      // blocked panel kernel (one exchange per 8 columns, stage1_panel_blk.cu) where the shape allows
     int panel_chol = 1;                     // Cholesky-QR panel with reconstructed Householder vectors (stage1_panel_chol.cu); env SVDB200_PANEL_CHOL=0: off
+    int pipe_chol = 0;                      // ... also for stage 1 beside resident stage-2 grids (list pipeline; SVDB200_PIPE_CHOL=1): measured slower there (its kernels disturb the latency-bound stage-2 chains: 2896 -> 2211-2551 GFLOP/s on the bench sweep)
     void* chol_ws = nullptr;                // its workspace: status word, [M1 | M2], partial Gram matrices (1 MB)
     double chol_guard = 1e-3;               // smallest accepted pivot ratio R_jj^2 / G_jj; below, the exchange-based kernels redo the panel
     const int* panel_run_if = nullptr;      // set while a gated fallback panel launch is being enqueued

@@ -635,9 +635,19 @@ chol_apply_kernel(T* __restrict__ A, size_t lda, int row0, int m, const T* __res
 }
 
 struct GramShape { int rows, ng, cs, np; };
-inline GramShape gram_shape(int mrows, int num_sms) {
+// small: beside resident stage-2 grids (list pipeline) -- at most 32 CTAs and no cluster, so that the launch needs no group of
+// free SMs in one GPC
+inline GramShape gram_shape(int mrows, int num_sms, bool small = false) {
     GramShape g;
     if (mrows <= 0) { g.rows = 8; g.ng = 0; g.cs = 1; g.np = 0; return g; }
+    if (small) {
+        const int target = std::max(1, std::min(18, (mrows + 127) / 128));
+        g.rows = ((mrows + target - 1) / target + 7) / 8 * 8;
+        g.ng = (mrows + g.rows - 1) / g.rows;
+        g.cs = 1;
+        g.np = g.ng;
+        return g;
+    }
     const int target = std::max(1, std::min(num_sms / kGramCluster * kGramCluster, (mrows + 63) / 64));
     g.rows = ((mrows + target - 1) / target + 7) / 8 * 8;
     g.ng = (mrows + g.rows - 1) / g.rows;
@@ -676,7 +686,7 @@ int launch_chol(Ctx* c, T* a, size_t lda, int m, T* V, T* V2, cudaStream_t strea
     int* status = reinterpret_cast<int*>(ws);
     T* mcat = reinterpret_cast<T*>(ws + 256);
     double* part = reinterpret_cast<double*>(ws + 256 + 64 * 128 * 8);
-    const GramShape g = gram_shape(m - B, c->num_sms);
+    const GramShape g = gram_shape(m - B, c->num_sms, c->overlap_safe != 0);
     SVDB_TRY((gram_launch<T, kTrans, B>(c, a, lda, B, m, part, g, stream)));
     {
         auto kern = chol_algebra_kernel<T, kTrans, B>;
@@ -705,6 +715,7 @@ int launch_chol(Ctx* c, T* a, size_t lda, int m, T* V, T* V2, cudaStream_t strea
 template <typename T, bool kTrans>
 int launch_panel_chol(Ctx* c, T* a, size_t lda, int m, int b, T* V, T* V2, cudaStream_t stream) {
     if (!c->chol_ws || m < 2 * b) return 1;
+    if (c->overlap_safe && !c->pipe_chol) return 1;
     switch (b) {
         case 8: return launch_chol<T, kTrans, 8>(c, a, lda, m, V, V2, stream);
         case 16: return launch_chol<T, kTrans, 16>(c, a, lda, m, V, V2, stream);
