@@ -634,6 +634,16 @@ chol_apply_kernel(T* __restrict__ A, size_t lda, int row0, int m, const T* __res
     }
 }
 
+// cudaFuncSetAttribute costs ~1 us of host time per call: once per kernel instantiation and device
+template <class K>
+inline cudaError_t smem_attr_once(Ctx* c, K kern, size_t smem, bool (&done)[16]) {
+    const int dev = c->device & 15;
+    if (done[dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
 struct GramShape { int rows, ng, cs, np; };
 // small: beside resident stage-2 grids (list pipeline) -- at most 32 CTAs and no cluster, so that the launch needs no group of
 // free SMs in one GPC
@@ -662,7 +672,7 @@ int gram_launch(Ctx* c, const T* a, size_t lda, int row0, int m, double* part, c
     constexpr int NB8 = B / 8, NE = NB8 * (NB8 + 1) / 2 * 64;
     auto kern = chol_gram_kernel<T, kTrans, NB8>;
     const size_t smem = (size_t)kGramWarps * NE * sizeof(double);
-    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.ng);
     cfg.blockDim = dim3(kGramThreads);
@@ -691,7 +701,7 @@ int launch_chol(Ctx* c, T* a, size_t lda, int m, T* V, T* V2, cudaStream_t strea
     {
         auto kern = chol_algebra_kernel<T, kTrans, B>;
         const size_t smem = chol_algebra_smem(B);
-        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         const size_t ldv2r = kTrans ? 1 : (size_t)B, ldv2c = kTrans ? (size_t)m : 1;
         kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, V, V2, ldv2r, ldv2c, mcat, status, c->chol_guard);
         c->launches++;
@@ -699,7 +709,7 @@ int launch_chol(Ctx* c, T* a, size_t lda, int m, T* V, T* V2, cudaStream_t strea
     {
         auto kern = chol_apply_kernel<T, kTrans, B>;
         const size_t smem = chol_apply_smem(B, sizeof(T));
-        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         const size_t ldv2r = kTrans ? 1 : (size_t)B, ldv2c = kTrans ? (size_t)m : 1;
         const int grid = (m - B + kApplyRows - 1) / kApplyRows;
         kern<<<grid, kApplyThreads, smem, stream>>>(a, lda, B, m, mcat, V, V2, ldv2r, ldv2c, status);
@@ -781,7 +791,7 @@ int dist_lq_finish(Ctx* c, T* a2, size_t ldl, int row0, int ncl, bool own_top, c
     {
         auto kern = chol_algebra_kernel<T, true, B>;
         const size_t smem = chol_algebra_smem(B);
-        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         if (own_top)
             kern<<<1, kAlgThreads, smem, stream>>>(a2, ldl, buf + NE, buf, 1, ut_loc, u2_loc, (size_t)1, (size_t)ncl, mcat, status, c->chol_guard);
         else
@@ -792,7 +802,7 @@ int dist_lq_finish(Ctx* c, T* a2, size_t ldl, int row0, int ncl, bool own_top, c
     if (ncl > row0) {
         auto kern = chol_apply_kernel<T, true, B>;
         const size_t smem = chol_apply_smem(B, sizeof(T));
-        SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         const int grid = (ncl - row0 + kApplyRows - 1) / kApplyRows;
         kern<<<grid, kApplyThreads, smem, stream>>>(a2, ldl, row0, ncl, mcat, ut_loc, u2_loc, (size_t)1, (size_t)ncl, status);
         c->launches++;
@@ -893,7 +903,7 @@ int dist_qr_owner(Ctx* c, T* a, size_t lda, int m, T* qsend, cudaStream_t stream
     SVDB_TRY((gram_launch<T, false, B>(c, a, lda, B, m, part, g, stream)));
     auto kern = chol_algebra_kernel<T, false, B>;
     const size_t smem = chol_algebra_smem(B);
-    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
     kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
     c->launches++;
     const size_t tot = (size_t)(m - B) * B;
@@ -927,7 +937,7 @@ int dist_qr_owner_early(Ctx* c, T* a, size_t lda, int m, T* qsend, int phase, cu
     SVDB_TRY((gram_launch<T, false, B>(c, raw, (size_t)B, 0, m - B, part, g, stream)));
     auto kern = chol_algebra_kernel<T, false, B>;
     const size_t smem = chol_algebra_smem(B);
-    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
     kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
     c->launches++;
     qr_zero_kernel<T><<<blocks, 256, 0, stream>>>(a, lda, m, B, flag, status);
@@ -945,7 +955,7 @@ int dist_qr_all(Ctx* c, T* qsend, int m, T* V, T* V2, cudaStream_t stream) {
     c->launches++;
     auto kern = chol_apply_kernel<T, false, B>;
     const size_t smem = chol_apply_smem(B, sizeof(T));
-    SVDB_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
     const int grid = (m - B + kApplyRows - 1) / kApplyRows;
     kern<<<grid, kApplyThreads, smem, stream>>>(raw, (size_t)B, 0, m - B, mcat, V + (size_t)B * B, V2 + (size_t)B * B, (size_t)B, (size_t)1, status);
     c->launches++;
