@@ -421,7 +421,8 @@ def dist_stage1_config(args, capi, torch, dist, stream, dev, local_rank, rank, w
     try:
         uid = D.exchange_unique_id(rank, world)
         out.update(one(world, rank, uid, 2))
-        out["collectives"] = ("per block step: ncclBroadcast([V | V S^T]) of the QR panel, ncclAllReduce([Gram | top block], 50 KB, double) of the "
+        out["collectives"] = ("per block step: ncclBroadcast(raw QR panel rows, (m-b) b elements, third stream, beside the owner's factorisation) + "
+                              "ncclBroadcast([M1 | M2], top blocks, status: 4 b^2 + 4 elements), ncclAllReduce([Gram | top block], 50 KB, double) of the "
                               "distributed LQ panel, ncclAllReduce(W)") if world > 1 else "none (one rank)"
         if world > 1 and not os.environ.get("SKIP_N1"):
             t1 = torch.zeros(1, device=dev, dtype=torch.float64)
