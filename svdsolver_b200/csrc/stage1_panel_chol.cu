@@ -13,7 +13,8 @@
 //     A1 - S R = L U~                               LU without pivoting of (Q1 - S) R; s_i = -sign(pivot_i) is chosen while
 //                                                   eliminating (|pivot| >= R_ii: no growth), U~ = U R
 //     Y  = [L; A2 U~^-1]                            the Householder vectors;  R_hh = S R
-//     T^-1 = diag(Y^T Y)/2 + striu(Y^T Y),          Y^T Y = L^T L + M1^T G2 M1, M1 = U~^-1   (all b x b, in double)
+//     T^-1 = diag(Y^T Y)/2 + striu(Y^T Y)           = -L^T S U^-1 because Q = P R^-1 is orthonormal (the paper's T = -U S L^-T);
+//                                                   U^-1 = R M1, M1 = U~^-1                  (all b x b, in double)
 //     V2 = -Y T^T = [-L T^T ; A2 M2], M2 = -M1 T^T                                           -- chol_algebra_kernel (1 CTA)
 //     [Y2 | V2_2] = A2 [M1 | M2]                    second pass, rows independent             -- chol_apply_kernel
 // Two passes over the panel + O(b^3) work on one SM instead of b (or b/8) grid-wide exchanges: the time no longer grows
@@ -242,7 +243,7 @@ chol_algebra_kernel(T* __restrict__ top, size_t ldt, const double* __restrict__ 
     double* rdiag = gdiag + B;
     double* sgn = rdiag + B;
     double* dinv = sgn + B;
-    double* sc = dinv + B;           // 2 x 8 scalars of the elimination step (double-buffered), then 6 x B pivot row / column buffers
+    double* sc = dinv + B;           // 32 step scalars (ring buffers), then 8 x BP doubles of pivot row / column buffers
     int* ctl = reinterpret_cast<int*>(sc + 32 + 8 * (B < 32 ? 32 : B));
     const int tid = threadIdx.x;
     long long tick = SVDB_PANEL_TIMING ? clock64() : 0;
@@ -304,14 +305,17 @@ chol_algebra_kernel(T* __restrict__ top, size_t ldt, const double* __restrict__ 
     if (tid < B) gdiag[tid] = Gc[tid * LD + tid];
     CHOL_TICK(1);
     // ---- Cholesky (as a square-root-free elimination; row i of R is row i of the reduced matrix / sqrt(g_ii)) and the LU
-    //      factorisation of A1 - S R, one column per step, ONE barrier per step.  The loop is bound by the dependent chain of
-    //      the step scalars (an FP64 operation has ~40 cycles of latency here; measured: ~30 dependent operations per step
-    //      cost 1000-1300 cycles whatever the thread layout), so the chain is cut into three that run side by side:
+    //      factorisation of A1 - S R, one column per step, ONE barrier per step.  The loop is bound by latency: the dependent
+    //      chain of the step scalars (tools/probes/fp64_latency.cu on this GPU: DFMA 8, 1/x 82, rsqrt 77, barrier + hand-over
+    //      through shared memory 113 cycles) and each warp's own instruction stream.  Hence:
     //        * both matrices stay in registers for the whole elimination (row k on warp k % 16, column j on lane j % 32); per
     //          step only the pivot rows and the pivot column of W go through shared memory, published by their owners;
-    //        * iteration t runs Cholesky step t (chain: update, 1/g), a helper lane that forms sqrt(g_tt) (and the guard), and
-    //          LU step t-2 (chain: update, pivot = w - s sqrt(g), 1/pivot) -- three different warps;
-    //        * an owner warp updates the row it has to publish first, and does the part it owns first. ------------------------------
+    //        * the chain is cut into three that run on different warps: iteration t runs Cholesky step t (update, 1/g), a
+    //          helper lane that forms sqrt(g_tt) (and the guard), and LU step t-2 (update, pivot = w - s sqrt(g), 1/pivot);
+    //        * an owner warp updates the row it has to publish first, and does the part it owns first;
+    //        * the updates are unconditional (no per-element predicates): finished rows / columns become garbage that is
+    //          never published.
+    //      Measured 900 (b = 32) / 1370 (b = 64) cycles per step; profiles/r02_summary.md has the history. ---------------------------
     constexpr int NW = kAlgThreads / 32;
     constexpr int RPW = B >= NW ? B / NW : 1, CPT = B >= 32 ? B / 32 : 1;
     constexpr int BP = B < 32 ? 32 : B;      // padded row length of the exchange buffers (lanes beyond B read / write padding)
