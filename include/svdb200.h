@@ -123,6 +123,11 @@ int svdb200_bidiagonalize_many_f32(svdb200_handle h, size_t count, float* const*
 int svdb200_bidiagonalize_many_f64(svdb200_handle h, size_t count, double* const* a, const size_t* n, size_t band, int order, double* const* d, double* const* e);
 int svdb200_bidiagonalize_many_dev_f32(svdb200_handle h, size_t count, float* const* a_dev, const size_t* n, size_t band, int order, float* const* d_dev, float* const* e_dev);
 int svdb200_bidiagonalize_many_dev_f64(svdb200_handle h, size_t count, double* const* a_dev, const size_t* n, size_t band, int order, double* const* d_dev, double* const* e_dev);
+/* How svdb200_bidiagonalize_many_* schedules a list on `lanes` chains (pure host function, no handle, no device): the matrices
+ * are partitioned over the chains longest-processing-time-first (a chain is bound by its stage-2 kernel, whose time is
+ * proportional to n), run in ascending size inside a chain and are issued alternating between the chains.  order_out[j] =
+ * index of the j-th matrix issued, chain_out[j] = its chain.  The results of the list calls do not depend on the schedule. */
+int svdb200_list_plan(int lanes, size_t count, const size_t* n, size_t* order_out, int* chain_out);
 
 /* ---- Fused chain: singular values of a dense matrix ------------------------------
  * dense -> brd_p1 -> brd_p2 -> qrd.  `a` is overwritten by the bidiagonalised matrix. */

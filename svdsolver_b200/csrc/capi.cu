@@ -406,7 +406,8 @@ static int drain_into(Ctx* c, cudaStream_t into) {
 // stage-1 factorizations and `lanes` sweep pipelines are in flight (default 2; 4 measured slower: contention); within a chain stage 1 of the next matrix starts as soon
 // as the previous stage 1 is done, beside that matrix's stage 2.  `h2d` (host variant): copy issued on the chain's stream.
 template <typename T>
-static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, size_t band, int order, T* d, T* e, cudaStream_t* lane_out) {
+static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, size_t band, int order, T* d, T* e, cudaStream_t* lane_out,
+                        int chain) {
     const bool overlap = order == SVDB200_ORDER_PANEL && n <= kOverlapMaxN && !c->profile;
     const int nl = overlap ? lanes_for(c, n, band) : 1;
     if (!overlap || nl == 1) {
@@ -425,7 +426,7 @@ static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, s
         *lane_out = c->stream;
         return 0;
     }
-    const int k = (int)(i % (size_t)c->lanes);
+    const int k = chain % c->lanes;
     Ctx* s = c->s1ctx[k];
     inherit_settings(c, s);
     if (a_host) SVDB_CHECK(c, cudaMemcpyAsync(a_dev, a_host, sizeof(T) * n * n, cudaMemcpyHostToDevice, s->stream));
@@ -443,6 +444,37 @@ static int pipeline_one(Ctx* c, size_t i, T* a_dev, const T* a_host, size_t n, s
     return 0;
 }
 
+// Which chain works on which matrix, and in which order the matrices are issued.  The chains are bound by their stage-2 lanes
+// (stage-2 time ~ n), so the matrices are partitioned by longest-processing-time-first over the chains; inside a chain they
+// run in ascending size, and the issue order alternates between the chains.  (The reference's benchmark list is ascending:
+// dealing it out i % lanes leaves the last chain 8 % longer than the first.)  Results do not depend on the order.
+struct ListPlan { std::vector<size_t> order; std::vector<int> chain; };
+static ListPlan plan_list(int lanes, size_t count, const size_t* n) {
+    ListPlan pl;
+    const int L = lanes < 1 ? 1 : lanes;
+    pl.order.reserve(count); pl.chain.reserve(count);
+    if (L == 1 || count <= (size_t)L) {
+        for (size_t i = 0; i < count; ++i) { pl.order.push_back(i); pl.chain.push_back((int)(i % (size_t)L)); }
+        return pl;
+    }
+    std::vector<size_t> idx(count);
+    for (size_t i = 0; i < count; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return n[x] > n[y]; });
+    std::vector<std::vector<size_t>> items(L);
+    std::vector<size_t> load(L, 0);
+    for (size_t i : idx) {
+        int best = 0;
+        for (int l = 1; l < L; ++l) if (load[l] < load[best]) best = l;
+        items[best].push_back(i);
+        load[best] += n[i];
+    }
+    for (auto& v : items) std::stable_sort(v.begin(), v.end(), [&](size_t x, size_t y) { return n[x] != n[y] ? n[x] < n[y] : x < y; });
+    for (size_t t = 0; pl.order.size() < count; ++t)
+        for (int l = 0; l < L; ++l)
+            if (t < items[l].size()) { pl.order.push_back(items[l][t]); pl.chain.push_back(l); }
+    return pl;
+}
+
 template <typename T>
 int bidiagonalize_many_dev(Ctx* c, size_t count, T* const* a, const size_t* n, size_t band, int order, T* const* d, T* const* e) {
     if (count == 0) return 0;
@@ -453,9 +485,11 @@ int bidiagonalize_many_dev(Ctx* c, size_t count, T* const* a, const size_t* n, s
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s2_stream[l], c->s2ev[0], 0));
         SVDB_CHECK(c, cudaStreamWaitEvent(c->s1ctx[l]->stream, c->s2ev[0], 0));
     }
-    for (size_t i = 0; i < count; ++i) {
+    const ListPlan pl = plan_list(c->lanes, count, n);
+    for (size_t j = 0; j < count; ++j) {
+        const size_t i = pl.order[j];
         cudaStream_t lane;
-        SVDB_TRY(pipeline_one<T>(c, i, a[i], (const T*)nullptr, n[i], band, order, d ? d[i] : nullptr, e ? e[i] : nullptr, &lane));
+        SVDB_TRY(pipeline_one<T>(c, i, a[i], (const T*)nullptr, n[i], band, order, d ? d[i] : nullptr, e ? e[i] : nullptr, &lane, pl.chain[j]));
     }
     const int sj = drain_into(c, s0);                                 // join
     c->band_capture.clear();
@@ -515,26 +549,32 @@ int bidiagonalize_many_host(Ctx* c, size_t count, T* const* a, const size_t* n, 
         return 0;
     };
     int st = 0;
-    for (size_t i = 0; i < count && st == 0; ++i) {
-        const int k = (int)(i % NB);                                  // chain i % kLanes alternates between its two buffers
+    const ListPlan pl = plan_list(c->lanes, count, n);
+    size_t per_chain[Ctx::kLanes] = {};
+    bool used[NBmax] = {};
+    for (size_t j = 0; j < count && st == 0; ++j) {
+        const size_t i = pl.order[j];
+        const int ch = pl.chain[j] % c->lanes;
+        const int k = ch + c->lanes * (int)(per_chain[ch]++ % 2);     // a chain alternates between its two staging buffers
         const size_t ni = n[i];
         T* buf = reinterpret_cast<T*>(c->a_stage[k]);
         T* dd = reinterpret_cast<T*>(c->de2) + (size_t)2 * k * (c->max_n + 8);
         T* ee = dd + (c->max_n + 8);
         if ((st = copy_back(k)) != 0) break;                          // a deferred (pageable) result still sitting in this buffer
-        if (i >= (size_t)NB) {                                        // the copy into the buffer is issued on the chain's stage-1 stream
-            cudaError_t we = cudaStreamWaitEvent(c->s1ctx[i % (size_t)c->lanes]->stream, ev_free[k], 0);
+        if (used[k]) {                                                // the copy into the buffer is issued on the chain's stage-1 stream
+            cudaError_t we = cudaStreamWaitEvent(c->s1ctx[ch]->stream, ev_free[k], 0);
             if (we == cudaSuccess) we = cudaStreamWaitEvent(s0, ev_free[k], 0);
             if (we != cudaSuccess) { st = cuda_status(c, we, "cudaStreamWaitEvent"); break; }
         }
+        used[k] = true;
         cudaStream_t lane = s0;
-        st = pipeline_one<T>(c, i, buf, a[i], ni, band, order, dd, ee, &lane);
+        st = pipeline_one<T>(c, i, buf, a[i], ni, band, order, dd, ee, &lane, ch);
         if (st != 0) break;
         res[k] = Result{a[i], d ? d[i] : nullptr, e ? e[i] : nullptr, ni, lane, true};
         const bool defer = is_pageable(a[i]) || is_pageable(res[k].d) || is_pageable(res[k].e);
         if (!defer && (st = copy_back(k)) != 0) break;
     }
-    for (int j = 0; j < NB && st == 0; ++j) st = copy_back((int)((count + (size_t)j) % (size_t)NB));   // oldest first
+    for (int j = 0; j < NB && st == 0; ++j) st = copy_back(j);       // whatever is still deferred
     int sj = drain_into(c, s0);
     c->band_capture.clear();
     cudaError_t es = cudaStreamSynchronize(s0);                       // host buffers are valid on return
@@ -1042,6 +1082,12 @@ int svdb200_debug_stage2_timing(long long* out16) { return out16 ? stage2_debug_
 int svdb200_debug_stage2_fast_timing(long long* out16) { return out16 ? stage2_fast_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_timing(long long* out16) { return out16 ? panel_reg_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_debug_panel_blk_timing(long long* out16) { return out16 ? panel_blk_debug_read(out16) : SVDB200_E_ARG; }
+int svdb200_list_plan(int lanes, size_t count, const size_t* n, size_t* order_out, int* chain_out) {
+    if (lanes < 1 || lanes > Ctx::kLanes || (count > 0 && (!n || !order_out || !chain_out))) return SVDB200_E_ARG;
+    const ListPlan pl = plan_list(lanes, count, n);
+    for (size_t j = 0; j < count; ++j) { order_out[j] = pl.order[j]; chain_out[j] = pl.chain[j]; }
+    return 0;
+}
 int svdb200_debug_panel_chol_timing(long long* out16) { return out16 ? panel_chol_debug_read(out16) : SVDB200_E_ARG; }
 int svdb200_set_panel_kernel(svdb200_handle h, int blocked) {
     if (!h || blocked < 0 || blocked > 2) return SVDB200_E_ARG;

@@ -59,3 +59,44 @@ def test_dist_local_cols(built):
     Z = ctypes.c_size_t
     tot = sum(lib.svdb200_dist_local_cols(Z(1024), Z(32), ctypes.c_int(r), ctypes.c_int(3)) for r in range(3))
     assert tot == 1024
+
+
+def test_list_plan_balances_the_chains():
+    """svdb200_list_plan (host logic of svdb200_bidiagonalize_many_*): every matrix exactly once, chains balanced by
+    longest-processing-time-first (the reference's ascending benchmark list dealt out i % 2 leaves one chain 8 % longer),
+    ascending sizes inside a chain, alternating issue order; degenerate inputs keep the caller's order."""
+    import ctypes
+    from svdsolver_b200 import capi
+    lib = capi.lib()
+
+    def plan(lanes, sizes):
+        cnt = len(sizes)
+        n = (ctypes.c_size_t * cnt)(*sizes)
+        order = (ctypes.c_size_t * cnt)()
+        chain = (ctypes.c_int * cnt)()
+        assert lib.svdb200_list_plan(ctypes.c_int(lanes), ctypes.c_size_t(cnt), n, order, chain) == 0
+        return list(order), list(chain)
+
+    sizes = list(range(320, 3841, 320))                           # BASELINE configs[1]
+    order, chain = plan(2, sizes)
+    assert sorted(order) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i, c in zip(order, chain) if c == l) for l in (0, 1)]
+    assert loads[0] == loads[1] == sum(sizes) // 2                # 12480 / 12480 (i % 2 gives 11520 / 13440)
+    for l in (0, 1):
+        mine = [sizes[i] for i, c in zip(order, chain) if c == l]
+        assert mine == sorted(mine)
+    assert chain[:4] == [0, 1, 0, 1]
+    # all sizes equal: round robin in the caller's order
+    order, chain = plan(2, [512] * 6)
+    assert order == list(range(6)) and chain == [0, 1, 0, 1, 0, 1]
+    # fewer matrices than chains, one chain, empty list
+    assert plan(4, [640, 320]) == ([0, 1], [0, 1])
+    assert plan(1, [640, 320, 960]) == ([0, 1, 2], [0, 0, 0])
+    assert plan(2, []) == ([], [])
+    assert lib.svdb200_list_plan(ctypes.c_int(0), ctypes.c_size_t(0), None, None, None) != 0
+    # three chains, ragged sizes: every matrix once, loads within the largest matrix of each other
+    sizes = [64, 1280, 96, 640, 128, 512, 320, 2048, 32]
+    order, chain = plan(3, sizes)
+    assert sorted(order) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i, c in zip(order, chain) if c == l) for l in range(3)]
+    assert max(loads) - min(loads) <= max(sizes)
