@@ -7,9 +7,10 @@
 // The Householder QR factorisation of a full-rank panel is unique once the sign rule is fixed, so it can be obtained from
 // ANY QR factorisation (Ballard, Demmel, Grigori, Jacquelin, Nguyen, Solomonik: "Reconstructing Householder vectors from
 // tall-skinny QR", 2014).  With P = [A1; A2] (A1 = top b x b block):
-//     G2 = A2^T A2                                  one pass over the panel, DMMA (mma.sync.m8n8k4.f64), exact products of
+//     G  = P^T P                                    one pass over the panel, DMMA (mma.sync.m8n8k4.f64), exact products of
 //                                                   the elements in double, deterministic reduction      -- chol_gram_kernel
-//     G  = G2 + A1^T A1 = R^T R                     Cholesky (R upper, positive diagonal), P = Q R
+//                                                   (the distributed QR panel sums the rows below A1 and adds A1^T A1 later)
+//     G  = R^T R                                    Cholesky (R upper, positive diagonal), P = Q R
 //     A1 - S R = L U~                               LU without pivoting of (Q1 - S) R; s_i = -sign(pivot_i) is chosen while
 //                                                   eliminating (|pivot| >= R_ii: no growth), U~ = U R
 //     Y  = [L; A2 U~^-1]                            the Householder vectors;  R_hh = S R
@@ -217,7 +218,8 @@ __device__ __forceinline__ void tri_inv_upper(FU u, double* __restrict__ X, doub
 constexpr size_t chol_algebra_smem(int b) { return ((size_t)6 * b * (b + 1) + 4 * b + 8 * (b < 32 ? 32 : b) + 64) * sizeof(double); }
 
 // ---- the b x b algebra: one CTA ------------------------------------------------------------------------------------------
-// part: np tile-packed partial Gram matrices of the rows >= b (np == 0: G2 = 0); top: the b x b top block in panel
+// part: np tile-packed partial Gram matrices -- of the rows >= b when add_top != 0 (the kernel then adds A1^T A1), of all rows
+// otherwise (np == 0: zero); top: the b x b top block in panel
 // coordinates, element (r, c) at top[r*ldt + c] (kTopT == false) or top[c*ldt + r] (kTopT == true), overwritten with R_hh
 // (exact zeros below the diagonal); top_d != nullptr: the input top block comes from there instead (dense, double, r*B + c:
 // the distributed LQ panel, where it arrives with the all-reduced Gram matrix).  vtop / v2top receive the top b rows of V
@@ -230,7 +232,7 @@ template <typename T, bool kTopT, int B>
 __global__ void __launch_bounds__(kAlgThreads, 1)
 chol_algebra_kernel(T* __restrict__ top, size_t ldt, const double* __restrict__ top_d, const double* __restrict__ part, int np,
                     T* __restrict__ vtop, T* __restrict__ v2top, size_t ldv2r, size_t ldv2c, T* __restrict__ mcat, int* __restrict__ status,
-                    double guard) {
+                    double guard, int add_top) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LD = B + 1, NB8 = B / 8, NT = NB8 * (NB8 + 1) / 2, NE = NT * 64;
     double* Gc = reinterpret_cast<double*>(smem_raw);   // G2 -> G -> reduced Gram matrix (upper); R^T below the diagonal as rows finish
@@ -297,11 +299,13 @@ chol_algebra_kernel(T* __restrict__ top, size_t ldt, const double* __restrict__ 
     if (tid == 0) ctl[0] = 0;
     __syncthreads();
     CHOL_TICK(0);
-    // ---- G = G2 + A1^T A1 (upper tiles) -------------------------------------------------------------------------------------------
-    mm_dmma<B>(tid, kAlgThreads, [&](int i, int k) { return W[k * LD + i]; }, [&](int k, int j) { return W[k * LD + j]; },
-               [](int ti, int tj, int& k0, int& k1) { k0 = 0; k1 = B / 4; return tj >= ti; },
-               [&](int i, int j, double v) { Gc[i * LD + j] += v; });
-    __syncthreads();
+    // ---- G = G2 + A1^T A1 (upper tiles) -- only when pass 1 left the top block out (add_top); otherwise the partials are G already ----
+    if (add_top) {
+        mm_dmma<B>(tid, kAlgThreads, [&](int i, int k) { return W[k * LD + i]; }, [&](int k, int j) { return W[k * LD + j]; },
+                   [](int ti, int tj, int& k0, int& k1) { k0 = 0; k1 = B / 4; return tj >= ti; },
+                   [&](int i, int j, double v) { Gc[i * LD + j] += v; });
+        __syncthreads();
+    }
     if (tid < B) gdiag[tid] = Gc[tid * LD + tid];
     CHOL_TICK(1);
     // ---- Cholesky (as a square-root-free elimination; row i of R is row i of the reduced matrix / sqrt(g_ii)) and the LU
@@ -700,14 +704,14 @@ int launch_chol(Ctx* c, T* a, size_t lda, int m, T* V, T* V2, cudaStream_t strea
     int* status = reinterpret_cast<int*>(ws);
     T* mcat = reinterpret_cast<T*>(ws + 256);
     double* part = reinterpret_cast<double*>(ws + 256 + 64 * 128 * 8);
-    const GramShape g = gram_shape(m - B, c->num_sms, c->overlap_safe != 0);
-    SVDB_TRY((gram_launch<T, kTrans, B>(c, a, lda, B, m, part, g, stream)));
+    const GramShape g = gram_shape(m, c->num_sms, c->overlap_safe != 0);     // pass 1 over ALL rows: the partials sum to G itself
+    SVDB_TRY((gram_launch<T, kTrans, B>(c, a, lda, 0, m, part, g, stream)));
     {
         auto kern = chol_algebra_kernel<T, kTrans, B>;
         const size_t smem = chol_algebra_smem(B);
         { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         const size_t ldv2r = kTrans ? 1 : (size_t)B, ldv2c = kTrans ? (size_t)m : 1;
-        kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, V, V2, ldv2r, ldv2c, mcat, status, c->chol_guard);
+        kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, V, V2, ldv2r, ldv2c, mcat, status, c->chol_guard, 0);
         c->launches++;
     }
     {
@@ -752,8 +756,8 @@ int panel_chol_debug_read(long long* out16) {
 }
 
 // ---- distributed LQ panel (dist.cu): the b x n' row panel is spread over the ranks by columns = by panel rows ---------------
-// Every rank: Gram matrix of its local panel rows (the owner of the first trailing block leaves the top b x b block out and
-// contributes it as is) -> ONE all-reduce of [tile-packed G2 | A1] in double (dist.cu) -> the same b x b algebra on every
+// Every rank: Gram matrix of its local panel rows (the owner of the first trailing block also contributes the top b x b block
+// as is) -> ONE all-reduce of [tile-packed G2 | A1] in double (dist.cu) -> the same b x b algebra on every
 // rank (identical inputs => identical [M1 | M2]) -> second pass over the local rows, which leaves U^T and S U directly in
 // the rank's local layout.  No gather of the row panel, no redundant factorisation of an n'-wide panel.
 namespace {
@@ -776,8 +780,9 @@ int dist_lq_gram(Ctx* c, const T* a2, size_t ldl, int row0, int ncl, bool own_to
     constexpr int NB8 = B / 8, NE = NB8 * (NB8 + 1) / 2 * 64;
     char* ws = reinterpret_cast<char*>(c->chol_ws);
     double* part = reinterpret_cast<double*>(ws + 256 + 64 * 128 * 8);
-    const GramShape g = gram_shape(ncl - row0, c->num_sms);
-    if (g.ng > 0) SVDB_TRY((gram_launch<T, true, B>(c, a2, ldl, row0, ncl, part, g, stream)));
+    (void)row0;                                            // pass 1 covers all local rows (the top block's rows included: G, not G2)
+    const GramShape g = gram_shape(ncl, c->num_sms);
+    if (g.ng > 0) SVDB_TRY((gram_launch<T, true, B>(c, a2, ldl, 0, ncl, part, g, stream)));
     const int tot = NE + B * B;
     chol_pack_kernel<T, B><<<(tot + 255) / 256, 256, 0, stream>>>(part, g.np, own_top ? a2 : nullptr, ldl, buf);
     c->launches++;
@@ -797,10 +802,10 @@ int dist_lq_finish(Ctx* c, T* a2, size_t ldl, int row0, int ncl, bool own_top, c
         const size_t smem = chol_algebra_smem(B);
         { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
         if (own_top)
-            kern<<<1, kAlgThreads, smem, stream>>>(a2, ldl, buf + NE, buf, 1, ut_loc, u2_loc, (size_t)1, (size_t)ncl, mcat, status, c->chol_guard);
+            kern<<<1, kAlgThreads, smem, stream>>>(a2, ldl, buf + NE, buf, 1, ut_loc, u2_loc, (size_t)1, (size_t)ncl, mcat, status, c->chol_guard, 0);
         else
             kern<<<1, kAlgThreads, smem, stream>>>(scratch, (size_t)B, buf + NE, buf, 1, scratch + B * B, scratch + 2 * B * B, (size_t)1, (size_t)B,
-                                                   mcat, status, c->chol_guard);
+                                                   mcat, status, c->chol_guard, 0);
         c->launches++;
     }
     if (ncl > row0) {
@@ -908,7 +913,7 @@ int dist_qr_owner(Ctx* c, T* a, size_t lda, int m, T* qsend, cudaStream_t stream
     auto kern = chol_algebra_kernel<T, false, B>;
     const size_t smem = chol_algebra_smem(B);
     { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
-    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
+    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard, 1);
     c->launches++;
     const size_t tot = (size_t)(m - B) * B;
     int blocks = (int)std::min<size_t>((tot + 1023) / 1024, (size_t)4 * c->num_sms);
@@ -942,7 +947,7 @@ int dist_qr_owner_early(Ctx* c, T* a, size_t lda, int m, T* qsend, int phase, cu
     auto kern = chol_algebra_kernel<T, false, B>;
     const size_t smem = chol_algebra_smem(B);
     { static bool attr_done[16] = {}; SVDB_CHECK(c, smem_attr_once(c, kern, smem, attr_done)); }
-    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard);
+    kern<<<1, kAlgThreads, smem, stream>>>(a, lda, (const double*)nullptr, part, g.np, vtop, v2top, (size_t)B, (size_t)1, mcat, status, c->chol_guard, 1);
     c->launches++;
     qr_zero_kernel<T><<<blocks, 256, 0, stream>>>(a, lda, m, B, flag, status);
     c->launches++;
