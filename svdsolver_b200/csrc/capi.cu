@@ -402,7 +402,7 @@ static int drain_into(Ctx* c, cudaStream_t into) {
     return 0;
 }
 
-// One matrix through the pipeline.  Chain k = i % lanes: stage 1 on sub-handle k's streams, stage 2 on lane k -- so `lanes`
+// One matrix through the pipeline.  Chain k (chosen by plan_list): stage 1 on sub-handle k's streams, stage 2 on lane k -- so `lanes`
 // stage-1 factorizations and `lanes` sweep pipelines are in flight (default 2; 4 measured slower: contention); within a chain stage 1 of the next matrix starts as soon
 // as the previous stage 1 is done, beside that matrix's stage 2.  `h2d` (host variant): copy issued on the chain's stream.
 template <typename T>
